@@ -1,0 +1,171 @@
+/* trainner_b200 -- C ABI of the B200-native ESRGAN hot path (sm_100a).
+ *
+ * Drop-in boundary for the library calls the reference makes on its G/D training step
+ * (paths relative to victorca25/traiNNer codes/):
+ *   nn.Conv2d fwd / autograd dgrad / wgrad   models/modules/architectures/block.py:238
+ *   torch.cat + LeakyReLU + 0.2*x5+x          architectures/RRDBNet_arch.py:150-163 (fused epilogues)
+ *   F.interpolate(nearest x2)                 architectures/block.py:358         (store-replicate epilogue)
+ *   nn.BatchNorm2d (train)                    architectures/block.py:122
+ *   nn.MaxPool2d / ReLU / input-norm          architectures/perceptual.py:152-214
+ *   nn.L1Loss                                 models/losses.py:37-39
+ *
+ * Conventions: all pointers are DEVICE pointers owned by the caller (PyTorch allocator); the
+ * library never frees or retains them past the call.  Activations are NHWC bf16; images that
+ * cross the nn.Module boundary are NCHW fp32.  Every call enqueues on `stream` and returns
+ * without synchronising.  Return value 0 = ok, nonzero = error; message via
+ * b200_last_error() (thread-local).  No CPU fallback exists: on a machine without an sm_100
+ * device every compute entry point returns an error.
+ */
+#ifndef TRAINNER_B200_H_
+#define TRAINNER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b200_stream_t; /* cudaStream_t */
+
+#define B200_MAX_TAPS 16
+
+/* Implicit-GEMM convolution on tcgen05 tensor cores.  One descriptor covers fwd, dgrad
+ * (with weights packed [tap][ci][co]) and the parity-decomposed dgrad of stride-2 convs.
+ *   out[n, y*out_mul_y+out_off_y, x*out_mul_x+out_off_x, cout_off + co] = epilogue(
+ *       sum_t sum_ci in[n, y*in_stride+in_off_y+tap_dy[t], x*in_stride+in_off_x+tap_dx[t], cin_off+ci]
+ *                    * w[tap_w[t]][co][ci] )
+ * epilogue(v): v = alpha*(v + bias[co]) (+beta1*res1) (+beta2*res2) (+old out if accumulate)
+ *              -> lrelu(slope) if act -> times lrelu'(mask) for co in [mask_lo, mask_hi).     */
+typedef struct {
+  int32_t n, h_in, w_in;        /* input tensor [n, h_in, w_in, cx]                         */
+  int32_t cx, cin_off, cin;     /* input channel slice; cin % 16 == 0                       */
+  int32_t h_out, w_out;         /* logical output grid (before placement)                   */
+  int32_t h_buf, w_buf, cy;     /* output tensor [n, h_buf, w_buf, cy]                      */
+  int32_t cout_off, cout;       /* output channel slice; cout % 8 == 0                      */
+  int32_t ntaps;
+  int8_t tap_dy[B200_MAX_TAPS], tap_dx[B200_MAX_TAPS], tap_w[B200_MAX_TAPS];
+  int32_t in_stride, in_off_y, in_off_x;
+  int32_t out_mul_y, out_off_y, out_mul_x, out_off_x;
+  int32_t upsample2x;           /* 1: replicate every output to a 2x2 block (h_buf = 2*h_out) */
+  int32_t w_taps, w_cout_pad, w_cin_pad; /* packed weights [w_taps][w_cout_pad][w_cin_pad] bf16 */
+  float alpha;
+  int32_t act;                  /* 0 none, 1 leaky-relu(slope) (slope 0 = relu)             */
+  float slope;
+  float beta1, beta2;
+  int32_t res_nch;              /* residuals apply to co < res_nch                          */
+  int32_t res1_c, res1_coff, res2_c, res2_coff; /* res tensors [n, h_buf, w_buf, res_c] ([n,h_out,w_out,.] if upsample2x) */
+  int32_t accumulate;
+  int32_t mask_c, mask_coff, mask_lo, mask_hi;  /* mask tensor [n, h_buf, w_buf, mask_c]     */
+  float mask_slope;
+} b200_conv_desc;
+
+int b200_conv_igemm(const b200_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                    const void* res1, const void* res2, const void* mask, void* y,
+                    b200_stream_t stream);
+
+/* Weight gradient of a conv (autograd wgrad of block.py:238):
+ *   dw[co][ci][ky][kx] += scale * sum_{n,y,x} dy[n,y,x,dy_coff+co] * x[n, y*stride+ky-pad, x*stride+kx-pad, x_coff+ci]
+ * dw is fp32 OIHW (the layout of nn.Conv2d.weight.grad); accumulated with fp32 atomics.      */
+typedef struct {
+  int32_t n, h_in, w_in, cx, x_coff, cin;
+  int32_t h_out, w_out, cdy, dy_coff, cout;
+  int32_t kh, kw, stride, pad;
+  float scale;
+} b200_wgrad_desc;
+
+int b200_conv_wgrad(const b200_wgrad_desc* d, const void* x, const void* dy, float* dw,
+                    float* dbias, b200_stream_t stream);
+
+/* Pack fp32 OIHW conv weights into the bf16 tensor-core layouts, many tensors per launch.
+ * table: device array of b200_pack_entry.  mode 0: [tap][co][ci] (fwd); 1: [tap][ci][co] (dgrad) */
+typedef struct {
+  const float* src;  /* [cout][cin][kh*kw] */
+  void* dst;         /* bf16 [taps][rows_pad][cols_pad] */
+  int32_t cout, cin, taps, rows_pad, cols_pad, mode;
+  int32_t co_mul, co_off; /* source output channel = co * co_mul + co_off (pixel-shuffle groups); 0,0 = identity */
+} b200_pack_entry;
+
+int b200_pack_weights(const b200_pack_entry* table_dev, int32_t count, int32_t max_elems,
+                      b200_stream_t stream);
+
+/* 3x3 stride-1 pad-1 convolutions with a thin (<= 4 channel) side, CUDA-core direct kernels.
+ * thin->wide: x NCHW fp32 [n,cs,h,w] -> y NHWC bf16 [n,h,w,cy] slice, optional per-channel input
+ *             normalisation (x-mean)/std (perceptual.py:207) and lrelu/relu epilogue.
+ * wide->thin: x NHWC bf16 -> y NCHW fp32 [n,cs,h,w] (+bias).                                   */
+int b200_conv3x3_thin_to_wide(const float* x, const float* w_oihw, const float* bias, void* y,
+                              int32_t n, int32_t h, int32_t w, int32_t cs, int32_t cw, int32_t cy,
+                              int32_t y_coff, int32_t transpose_w, const float* mean,
+                              const float* std, int32_t act, float slope, const void* mask,
+                              int32_t mask_c, int32_t mask_coff, float mask_slope,
+                              b200_stream_t stream);
+int b200_conv3x3_wide_to_thin(const void* x, const float* w_oihw, const float* bias, float* y,
+                              int32_t n, int32_t h, int32_t w, int32_t cw, int32_t cx, int32_t x_coff,
+                              int32_t cs, int32_t transpose_w, const float* inv_std, float out_scale,
+                              b200_stream_t stream);
+/* wgrad of either: dw[cw_idx][cs_idx][3][3] (thin side fp32 NCHW, wide side bf16 NHWC).
+ * wide_is_out = 1: dw is [cw][cs][3][3] (thin->wide conv); 0: dw is [cs][cw][3][3].          */
+int b200_conv3x3_thin_wgrad(const float* thin, const void* wide, float* dw, float* dbias_wide,
+                            float* dbias_thin, int32_t n, int32_t h, int32_t w, int32_t cs,
+                            int32_t cw, int32_t cwide_buf, int32_t wide_coff, int32_t wide_is_out,
+                            const float* mean, const float* std, b200_stream_t stream);
+
+/* BatchNorm2d (training mode, batch statistics) + LeakyReLU on NHWC bf16 -- block.py:122,91.
+ * stats: fp32 [2][c] = sum, sumsq over n*h*w (zeroed by the call).                           */
+int b200_bn_stats(const void* z, float* stats, int64_t npix, int32_t c, b200_stream_t stream);
+int b200_bn_finalize(const float* stats, float* mean_invstd, float* running_mean,
+                     float* running_var, int64_t npix, int32_t c, float momentum, float eps,
+                     b200_stream_t stream);
+int b200_bn_apply_lrelu(const void* z, const float* mean_invstd, const float* gamma,
+                        const float* beta, void* a, int64_t npix, int32_t c, float slope,
+                        b200_stream_t stream);
+/* backward: da = grad wrt lrelu output.  Pass 1 reduces sums[2][c] = (sum dzhat, sum dzhat*zhat)
+ * (+ dgamma, dbeta when non-null); pass 2 writes dz.                                        */
+int b200_bn_bwd_reduce(const void* z, const void* da, const float* mean_invstd,
+                       const float* gamma, const float* beta, float* sums, int64_t npix, int32_t c,
+                       float slope, b200_stream_t stream);
+int b200_bn_bwd_apply(const void* z, const void* da, const float* mean_invstd, const float* gamma,
+                      const float* beta, const float* sums, void* dz, float* dgamma, float* dbeta,
+                      int64_t npix, int32_t c, float slope, b200_stream_t stream);
+
+/* MaxPool2d(2,2) on NHWC bf16 (perceptual.py:158) and its backward fused with the ReLU mask
+ * of the pooled activation.                                                                 */
+int b200_maxpool2x2(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c,
+                    b200_stream_t stream);
+int b200_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int32_t n, int32_t h, int32_t w,
+                        int32_t c, b200_stream_t stream);
+
+/* nearest x2 upsample backward: dx[n,y,x,c] = (sum of the 2x2 block of dy) * lrelu'(m) where m is
+ * read from mask_up[n,2y,2x,c] (the upsampled activation itself, [n,2h,2w,c]) when non-null.   */
+int b200_sumpool2x2_mask(const void* dy, const void* mask_up, void* dx, int32_t n, int32_t h,
+                         int32_t w, int32_t c, float slope, b200_stream_t stream);
+/* dst[p, dst_coff + c] += src[p, src_coff + c] on NHWC bf16 slices                              */
+int b200_add_slice_bf16(void* dst, int32_t dst_c, int32_t dst_coff, const void* src, int32_t src_c,
+                        int32_t src_coff, int64_t npix, int32_t c, b200_stream_t stream);
+
+/* L1 loss (mean |a-b|) forward + gradient in one pass -- losses.py:37-39.
+ * fp32 variant: a, b fp32, grad_a fp32 = gscale*sign(a-b)/numel.  bf16 variant likewise.
+ * loss_out: fp32 scalar accumulated with one atomic per block (zeroed by the call).        */
+int b200_l1_loss_f32(const float* a, const float* b, float* loss_out, float* grad_a, int64_t numel,
+                     float weight, b200_stream_t stream);
+int b200_l1_loss_bf16(const void* a, const void* b, float* loss_out, void* grad_a, int64_t numel,
+                      float weight, b200_stream_t stream);
+
+/* elementwise helpers */
+int b200_lrelu_mask_mul(const void* g, const void* y, void* out, int64_t numel, float slope,
+                        b200_stream_t stream);
+int b200_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t h, int32_t w,
+                               int32_t cy, int32_t y_coff, b200_stream_t stream);
+int b200_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t n, int32_t c, int32_t h, int32_t w,
+                               int32_t cx, int32_t x_coff, b200_stream_t stream);
+int b200_add_f32(float* dst, const float* src, int64_t numel, b200_stream_t stream);
+
+const char* b200_last_error(void);
+int b200_version(void);
+int b200_device_ok(void);   /* 1 if the current device is sm_100 */
+int64_t b200_launch_count(void);  /* kernels launched by this library since load */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRAINNER_B200_H_ */

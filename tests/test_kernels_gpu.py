@@ -1,0 +1,202 @@
+"""Kernel-level parity (B200): every CUDA entry point vs a plain PyTorch fp32 reference of the same op
+on bf16-rounded operands.  Tolerances: tensor-core convs accumulate in fp32 and round the output to
+bf16 once -> rel-L2 <= 4e-3 (bf16 output rounding is 2^-9 relative per element)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+def nhwc(x):  # NCHW fp32 -> NHWC bf16
+    return x.permute(0, 2, 3, 1).contiguous().to(BF)
+
+
+def nchw(x):  # NHWC bf16 -> NCHW fp32
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(BF).float()
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,s,p", [
+    (2, 24, 40, 64, 32, 3, 1, 1), (1, 16, 16, 96, 32, 3, 1, 1), (2, 20, 12, 160, 32, 3, 1, 1),
+    (1, 32, 32, 192, 64, 3, 1, 1), (2, 32, 32, 64, 64, 4, 2, 1), (4, 8, 8, 128, 256, 4, 2, 1),
+    (16, 8, 8, 512, 512, 3, 1, 1), (3, 4, 4, 64, 128, 3, 1, 1), (1, 64, 64, 64, 64, 3, 1, 1),
+])
+def test_conv_fwd(N, H, W, Cin, Cout, k, s, p):
+    from trainner_b200 import ops
+    x = rnd(N, Cin, H, W, seed=1)
+    w = rnd(Cout, Cin, k, k, scale=(2.0 / (Cin * k * k)) ** 0.5, seed=2)
+    b = rnd(Cout, scale=0.1, seed=3)
+    y = ops.conv2d(nhwc(x), w, b, stride=s, padding=p, act=1, slope=0.2)
+    ref = F.leaky_relu(F.conv2d(x, w, b, stride=s, padding=p), 0.2)
+    assert y.shape == (N, ref.shape[2], ref.shape[3], Cout)
+    assert rel(nchw(y), ref) < 4e-3
+
+
+def test_conv_fwd_slices_residual_upsample():
+    """channel-slice in/out (zero-copy concat), alpha*(conv+bias)+beta1*res1+beta2*res2, 2x2 store"""
+    from trainner_b200 import ops
+    N, H, W = 2, 16, 24
+    buf = rnd(N, 192, H, W, seed=4)
+    w = rnd(64, 96, 3, 3, scale=0.05, seed=5)
+    b = rnd(64, scale=0.1, seed=6)
+    r1, r2 = rnd(N, 192, H, W, seed=7), rnd(N, 64, H, W, seed=8)
+    out = torch.zeros(N, H, W, 128, dtype=BF, device="cuda")
+    ops.conv2d(nhwc(buf), w, b, cin_off=32, cin=96, out=out, cout_off=64, alpha=0.2, res1=nhwc(r1), res1_coff=0,
+               beta1=1.0, res2=nhwc(r2), beta2=0.5, res_nch=64)
+    ref = 0.2 * F.conv2d(buf[:, 32:128], w, b, padding=1) + r1[:, :64] + 0.5 * r2
+    assert rel(nchw(out)[:, 64:], ref) < 4e-3
+    assert float(out[..., :64].abs().max()) == 0.0
+    y = ops.conv2d(nhwc(buf[:, :64].contiguous()), w[:, :64].contiguous(), b, upsample2x=True)
+    ref = F.interpolate(F.conv2d(buf[:, :64], w[:, :64], b, padding=1), scale_factor=2.0, mode="nearest")
+    assert rel(nchw(y), ref) < 4e-3
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,s,p", [
+    (2, 24, 40, 64, 32, 3, 1, 1), (1, 16, 16, 192, 64, 3, 1, 1), (2, 32, 32, 64, 64, 4, 2, 1),
+    (4, 8, 8, 128, 256, 4, 2, 1), (2, 16, 16, 256, 512, 3, 1, 1),
+])
+def test_conv_dgrad(N, H, W, Cin, Cout, k, s, p):
+    from trainner_b200 import ops
+    x = rnd(N, Cin, H, W, seed=1).requires_grad_(True)
+    w = rnd(Cout, Cin, k, k, scale=(2.0 / (Cin * k * k)) ** 0.5, seed=2)
+    y = F.conv2d(x, w, None, stride=s, padding=p)
+    dy = rnd(*y.shape, seed=3)
+    y.backward(dy)
+    dx = ops.conv2d_dgrad(nhwc(dy), w, (H, W), stride=s, padding=p)
+    assert rel(nchw(dx), x.grad) < 4e-3
+
+
+def test_conv_dgrad_accumulate_mask():
+    from trainner_b200 import ops
+    N, H, W = 2, 16, 16
+    w = rnd(32, 96, 3, 3, scale=0.05, seed=2)
+    dbuf = rnd(N, 192, H, W, seed=3)     # gradient buffer: dY lives in channels [96,128)
+    fwd = rnd(N, 192, H, W, seed=4)      # forward buffer (mask source)
+    g = nhwc(dbuf).clone()
+    ops.conv2d_dgrad(g, w, (H, W), dy_coff=96, out=g, dx_coff=0, accumulate=True, mask=nhwc(fwd), mask_lo=64,
+                     mask_hi=96, mask_slope=0.2)
+    add = F.conv_transpose2d(dbuf[:, 96:128], w, padding=1)
+    ref = dbuf.clone()
+    ref[:, :96] = (dbuf[:, :96] + add)
+    ref[:, 64:96] = torch.where(fwd[:, 64:96] > 0, ref[:, 64:96], 0.2 * ref[:, 64:96])
+    assert rel(nchw(g)[:, :96], ref[:, :96]) < 5e-3
+    assert torch.equal(nchw(g)[:, 96:], dbuf[:, 96:])
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,s,p", [
+    (2, 24, 40, 64, 32, 3, 1, 1), (2, 16, 16, 192, 64, 3, 1, 1), (2, 32, 32, 64, 64, 4, 2, 1),
+    (4, 8, 8, 128, 256, 4, 2, 1), (16, 64, 64, 96, 32, 3, 1, 1),
+])
+def test_conv_wgrad(N, H, W, Cin, Cout, k, s, p):
+    from trainner_b200 import ops
+    x = rnd(N, Cin, H, W, seed=1)
+    w = rnd(Cout, Cin, k, k, scale=0.05, seed=2).requires_grad_(True)
+    b = torch.zeros(Cout, device="cuda", requires_grad=True)
+    y = F.conv2d(x, w, b, stride=s, padding=p)
+    dy = rnd(*y.shape, seed=3)
+    y.backward(dy)
+    dw, db = ops.conv2d_wgrad(nhwc(x), nhwc(dy), tuple(w.shape), stride=s, padding=p)
+    assert rel(dw, w.grad) < 2e-3
+    assert rel(db, b.grad) < 2e-3
+
+
+def test_thin_convs():
+    from trainner_b200 import ops
+    N, H, W = 2, 40, 52
+    x = torch.rand(N, 3, H, W, device="cuda")
+    w = rnd(64, 3, 3, 3, scale=0.2, seed=1)
+    b = rnd(64, scale=0.1, seed=2)
+    mean = torch.tensor([0.485, 0.456, 0.406], device="cuda")
+    std = torch.tensor([0.229, 0.224, 0.225], device="cuda")
+    y = ops.conv3x3_thin_to_wide(x, w, b, mean=mean, std=std, act=1, slope=0.0)
+    xn = (x - mean.view(1, 3, 1, 1)) / std.view(1, 3, 1, 1)
+    ref = F.relu(F.conv2d(xn, w, b, padding=1))
+    assert rel(nchw(y), ref) < 4e-3
+    # wide -> thin forward (HR_conv1) and the two input-gradient forms
+    xw = rnd(N, 64, H, W, seed=3)
+    w2 = rnd(3, 64, 3, 3, scale=0.05, seed=4)
+    b2 = rnd(3, scale=0.1, seed=5)
+    y2 = ops.conv3x3_wide_to_thin(nhwc(xw), w2, b2)
+    assert rel(y2, F.conv2d(xw, w2, b2, padding=1)) < 1e-4
+    dy = rnd(N, 64, H, W, seed=6)
+    xg = x.clone().requires_grad_(True)
+    F.conv2d(xg, w, b, padding=1).backward(dy)
+    dx = ops.conv3x3_wide_to_thin(nhwc(dy), w, None, transpose_w=True)
+    assert rel(dx, xg.grad) < 1e-4
+    dyt = torch.randn(N, 3, H, W, device="cuda")
+    xwg = xw.clone().requires_grad_(True)
+    F.conv2d(xwg, w2, b2, padding=1).backward(dyt)
+    dxw = ops.conv3x3_thin_to_wide(dyt, w2, None, transpose_w=True)
+    assert rel(nchw(dxw), xwg.grad) < 4e-3
+    # weight gradients
+    wg = w.clone().requires_grad_(True)
+    bg = b.clone().requires_grad_(True)
+    F.conv2d(x, wg, bg, padding=1).backward(dy)
+    dw, dbw, _ = ops.conv3x3_thin_wgrad(x, nhwc(dy), True, want_bias_wide=True)
+    assert rel(dw, wg.grad) < 1e-3 and rel(dbw, bg.grad) < 1e-3
+    w2g = w2.clone().requires_grad_(True)
+    b2g = b2.clone().requires_grad_(True)
+    F.conv2d(xw, w2g, b2g, padding=1).backward(dyt)
+    dw2, _, dbt = ops.conv3x3_thin_wgrad(dyt, nhwc(xw), False, want_bias_thin=True)
+    assert rel(dw2, w2g.grad) < 1e-3 and rel(dbt, b2g.grad) < 1e-3
+
+
+@pytest.mark.parametrize("N,H,W,C", [(4, 16, 16, 64), (2, 8, 8, 512), (16, 32, 32, 128)])
+def test_batchnorm_lrelu(N, H, W, C):
+    from trainner_b200 import ops
+    z = rnd(N, C, H, W, seed=1) * 1.5 + 0.3
+    z = z.to(BF).float()
+    gamma = (1 + 0.1 * torch.randn(C, device="cuda")).requires_grad_(True)
+    beta = (0.1 * torch.randn(C, device="cuda")).requires_grad_(True)
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    rm2, rv2 = rm.clone(), rv.clone()
+    zr = z.clone().requires_grad_(True)
+    ref = F.leaky_relu(F.batch_norm(zr, rm, rv, gamma, beta, True, 0.1, 1e-5), 0.2)
+    a, mi = ops.batchnorm_lrelu_train(nhwc(z), gamma.detach(), beta.detach(), rm2, rv2)
+    assert rel(nchw(a), ref) < 4e-3
+    assert rel(rm2, rm) < 1e-4 and rel(rv2, rv) < 1e-4
+    da = rnd(N, C, H, W, seed=2)
+    ref.backward(da)
+    dz, dg, dbt = ops.batchnorm_lrelu_backward(nhwc(z), nhwc(da), mi, gamma.detach(), beta.detach())
+    assert rel(nchw(dz), zr.grad) < 6e-3
+    assert rel(dg, gamma.grad) < 2e-3 and rel(dbt, beta.grad) < 2e-3
+
+
+def test_pools_and_l1():
+    from trainner_b200 import ops
+    x = F.relu(rnd(2, 64, 16, 24, seed=1))
+    y = ops.maxpool2x2(nhwc(x))
+    assert torch.equal(nchw(y), F.max_pool2d(x, 2, 2))
+    xr = x.clone().requires_grad_(True)
+    dy = rnd(2, 64, 8, 12, seed=2)
+    F.max_pool2d(xr, 2, 2).backward(dy)
+    dx = ops.maxpool2x2_backward(nhwc(x), nhwc(dy))
+    assert rel(nchw(dx), xr.grad * (x > 0)) < 1e-6
+    g = rnd(2, 64, 16, 24, seed=3)
+    m = rnd(2, 64, 16, 24, seed=4)
+    mu = F.interpolate(m[:, :, ::2, ::2], scale_factor=2.0, mode="nearest")
+    s = ops.sumpool2x2_mask(nhwc(g), nhwc(mu), 0.2)
+    ref = F.avg_pool2d(g, 2) * 4 * torch.where(m[:, :, ::2, ::2] > 0, 1.0, 0.2)
+    assert rel(nchw(s), ref) < 4e-3
+    a = torch.rand(4, 3, 64, 64, device="cuda", requires_grad=True)
+    b = torch.rand(4, 3, 64, 64, device="cuda")
+    l = F.l1_loss(a, b) * 0.01
+    l.backward()
+    loss, grad = ops.l1_loss_with_grad(a.detach(), b, 0.01)
+    assert abs(float(loss) - float(l)) < 1e-6 * max(1, abs(float(l))) + 1e-8
+    assert rel(grad, a.grad) < 1e-6
+    fa, fb = rnd(2, 16, 16, 512, seed=5).to(BF), rnd(2, 16, 16, 512, seed=6).to(BF)
+    loss, grad = ops.l1_loss_with_grad(fa, fb, 1.0)
+    assert abs(float(loss) - float((fa.float() - fb.float()).abs().mean())) < 1e-4

@@ -1,0 +1,452 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+//   D[pixel m (128 per tile), channel n (BN per tile)] = sum over taps t, channel chunks c of
+//       A_t,c [128 px x 64 ch]  (TMA 4-D box of the NHWC input, shifted by the tap, zero OOB fill,
+//                                SWIZZLE_128B, K-major)
+//     * B_t,c [BN co x 64 ch]   (TMA 3-D box of the packed weights [tap][co][ci], K-major)
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0      TMA producer (one elected lane issues), smem ring of `stages` {A,B} slots
+//   warp 1      TMEM allocator + tcgen05.mma issuer (one elected lane), fp32 accumulators in TMEM,
+//               two accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 2..5  epilogue: tcgen05.ld -> alpha/bias/residual/accumulate/LeakyReLU/mask -> bf16 ->
+//               128-bit stores into a channel slice of the NHWC output (zero-copy concat), optional
+//               2x2 store replication (nearest upsample folded into the store).
+//
+// Replaces, for the reference: nn.Conv2d fwd/dgrad (block.py:238), torch.cat (RRDBNet_arch.py:152-159),
+// LeakyReLU (block.py:91), x5*0.2+x (RRDBNet_arch.py:163,96), ShortcutBlock add (block.py:191),
+// F.interpolate nearest (block.py:358).
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kABytes = 128 * 128;  // 128 pixel rows x 64 bf16
+
+struct IgemmParams {
+  CUtensorMap in_map;
+  CUtensorMap w_map;
+  int tw, th, tn;
+  int tiles_x, tiles_y, tiles_n, n_blocks, total_tiles;
+  int Nimg, Ho, Wo;
+  int aux_h, aux_w, aux_my, aux_oy, aux_mx, aux_ox;  // grid of the residual / mask tensors
+  int in_stride, in_off_y, in_off_x;
+  int cin_off, k_chunks, last_k16;
+  int ntaps;
+  int8_t tap_dy[B200_MAX_TAPS], tap_dx[B200_MAX_TAPS], tap_w[B200_MAX_TAPS];
+  int BN, Cout;
+  int acc_cols;  // TMEM column stride between the two accumulator buffers
+  int stages;
+  uint32_t b_bytes;  // BN * 128 (TMA transaction bytes of one B slot)
+  uint32_t stage_bytes;
+  // output placement
+  __nv_bfloat16* out;
+  long long o_sn, o_sy, o_sx;
+  int o_coff, o_my, o_oy, o_mx, o_ox, upsample;
+  // epilogue
+  const float* bias;
+  float alpha;
+  int act;
+  float slope;
+  const __nv_bfloat16* res1;
+  const __nv_bfloat16* res2;
+  int res1_c, res1_coff, res2_c, res2_coff, res_nch;
+  float beta1, beta2;
+  int accumulate;
+  const __nv_bfloat16* mask;
+  int mask_c, mask_coff, mask_lo, mask_hi;
+  float mask_slope;
+};
+
+struct TileCoord {
+  int nb, x0, y0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
+  TileCoord t;
+  t.nb = tile % p.n_blocks;
+  int r = tile / p.n_blocks;
+  t.x0 = (r % p.tiles_x) * p.tw;
+  r /= p.tiles_x;
+  t.y0 = (r % p.tiles_y) * p.th;
+  t.n0 = (r / p.tiles_y) * p.tn;
+  return t;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+// Epilogue for NC (16 or 32) accumulator columns of one pixel row.
+template <int NC>
+__device__ __forceinline__ void epilogue_columns(const IgemmParams& p, const uint32_t* acc, int cbase,
+                                                 bool valid, long long pix_lin,
+                                                 __nv_bfloat16* out_px) {
+  if (!valid) return;
+#pragma unroll
+  for (int g = 0; g < NC / 8; ++g) {
+    const int c = cbase + g * 8;
+    if (c >= p.Cout) break;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
+    if (p.bias) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
+    if (c < p.res_nch) {
+      if (p.res1) {
+        float r[8];
+        unpack8(*reinterpret_cast<const uint4*>(p.res1 + pix_lin * p.res1_c + p.res1_coff + c), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(p.beta1, r[j], v[j]);
+      }
+      if (p.res2) {
+        float r[8];
+        unpack8(*reinterpret_cast<const uint4*>(p.res2 + pix_lin * p.res2_c + p.res2_coff + c), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(p.beta2, r[j], v[j]);
+      }
+    }
+    __nv_bfloat16* dst = out_px + p.o_coff + c;
+    if (p.accumulate) {
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(dst), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    if (p.act) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+    }
+    if (p.mask && c >= p.mask_lo && c < p.mask_hi) {
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(p.mask + pix_lin * p.mask_c + p.mask_coff + c), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = r[j] > 0.f ? v[j] : v[j] * p.mask_slope;
+    }
+    const uint4 o = pack8(v);
+    *reinterpret_cast<uint4*>(dst) = o;
+    if (p.upsample) {
+      *reinterpret_cast<uint4*>(dst + p.o_sx) = o;
+      *reinterpret_cast<uint4*>(dst + p.o_sy) = o;
+      *reinterpret_cast<uint4*>(dst + p.o_sy + p.o_sx) = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem =
+      reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tfull_bar[0], 1);
+    mbar_init(&tfull_bar[1], 1);
+    mbar_init(&tempty_bar[0], 4);
+    mbar_init(&tempty_bar[1], 4);
+    mbar_fence_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.in_map);
+    tma_prefetch_desc(&p.w_map);
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int k_iters = p.ntaps * p.k_chunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      for (int t = 0; t < p.ntaps; ++t) {
+        const int cx = tc.x0 * p.in_stride + p.in_off_x + p.tap_dx[t];
+        const int cy = tc.y0 * p.in_stride + p.in_off_y + p.tap_dy[t];
+        const int wt = p.tap_w[t];
+        for (int c = 0; c < p.k_chunks; ++c) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
+            uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+            mbar_expect_tx(&full_bar[stage], kABytes + p.b_bytes);
+            tma_load_4d(sa, &p.in_map, &full_bar[stage], p.cin_off + c * 64, cx, cy, tc.n0);
+            tma_load_3d(sa + kABytes, &p.w_map, &full_bar[stage], c * 64, tc.nb * p.BN, wt);
+          }
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
+    const uint64_t desc_hi = make_smem_desc(0, 16, 1024, LAYOUT_SW128, 0);
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem + acc * p.acc_cols;
+      int c = 0;
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const int nk = (c == p.k_chunks - 1) ? p.last_k16 : 4;
+        const uint32_t a_addr = smem_base + stage * p.stage_bytes;
+        const uint32_t b_addr = a_addr + kABytes;
+        if (elect_one()) {
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t ad = desc_hi | (uint64_t)(((a_addr + k * 32) >> 4) & 0x3FFF);
+            const uint64_t bd = desc_hi | (uint64_t)(((b_addr + k * 32) >> 4) & 0x3FFF);
+            umma_f16(d_tmem, ad, bd, idesc, (it | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++c == p.k_chunks) c = 0;
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;  // TMEM lane quadrant accessible by this warp
+    const int m = quad * 32 + lane;
+    const int ix = m % p.tw;
+    const int iy = (m / p.tw) % p.th;
+    const int in_ = m / (p.tw * p.th);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int x = tc.x0 + ix, y = tc.y0 + iy, n = tc.n0 + in_;
+      const bool valid = (x < p.Wo) && (y < p.Ho) && (n < p.Nimg);
+      // residual / mask tensors live on the output buffer's grid at the placed coordinates
+      // (or on the logical grid when the store replicates 2x2)
+      const long long pix_lin = ((long long)n * p.aux_h + (y * p.aux_my + p.aux_oy)) * p.aux_w +
+                                (x * p.aux_mx + p.aux_ox);
+      __nv_bfloat16* out_px = p.out + (long long)n * p.o_sn +
+                              (long long)(y * p.o_my + p.o_oy) * p.o_sy +
+                              (long long)(x * p.o_mx + p.o_ox) * p.o_sx;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem + ((uint32_t)(quad * 32) << 16) + acc * p.acc_cols;
+      const int cb = tc.nb * p.BN;
+      int c0 = 0;
+      for (; c0 + 32 <= p.BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c0, r);
+        tmem_ld_wait();
+        epilogue_columns<32>(p, r, cb + c0, valid, pix_lin, out_px);
+      }
+      if (c0 < p.BN) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_row + c0, r);
+        tmem_ld_wait();
+        epilogue_columns<16>(p, r, cb + c0, valid, pix_lin, out_px);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+inline int pow2_ceil(int v) {
+  int r = 1;
+  while (r < v) r <<= 1;
+  return r;
+}
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const void* w_packed,
+                               const float* bias, const void* res1, const void* res2,
+                               const void* mask, void* y, b200_stream_t stream) {
+  B200_REQUIRE(d && x && w_packed && y, "b200_conv_igemm: null argument");
+  B200_REQUIRE(d->cin > 0 && d->cin % 16 == 0, "b200_conv_igemm: cin=%d must be a multiple of 16", d->cin);
+  B200_REQUIRE(d->cout > 0 && d->cout % 8 == 0, "b200_conv_igemm: cout=%d must be a multiple of 8", d->cout);
+  B200_REQUIRE(d->cx % 8 == 0 && d->cy % 8 == 0 && d->cin_off % 8 == 0 && d->cout_off % 8 == 0,
+               "b200_conv_igemm: channel pitches/offsets must be multiples of 8");
+  B200_REQUIRE(d->ntaps >= 1 && d->ntaps <= B200_MAX_TAPS, "b200_conv_igemm: bad ntaps %d", d->ntaps);
+  B200_REQUIRE(d->in_stride >= 1 && d->in_stride <= 8, "b200_conv_igemm: bad in_stride");
+  B200_REQUIRE(d->w_cin_pad % 64 == 0 && d->w_cin_pad >= d->cin, "b200_conv_igemm: bad w_cin_pad");
+  B200_REQUIRE(d->w_cout_pad % 16 == 0 && d->w_cout_pad >= d->cout, "b200_conv_igemm: bad w_cout_pad");
+  B200_REQUIRE(!(d->upsample2x && (d->out_mul_y != 1 || d->out_mul_x != 1)),
+               "b200_conv_igemm: upsample2x excludes output placement");
+
+  static bool attr_set = false;
+  const int kSmemBytes = 200 * 1024;
+  if (!attr_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  // ---- tile geometry
+  p.tw = d->w_out > 8 ? 16 : (d->w_out > 4 ? 8 : 4);
+  int th_max = 128 / p.tw;
+  p.th = pow2_ceil(d->h_out) < th_max ? pow2_ceil(d->h_out) : th_max;
+  p.tn = 128 / (p.tw * p.th);
+  p.tiles_x = (d->w_out + p.tw - 1) / p.tw;
+  p.tiles_y = (d->h_out + p.th - 1) / p.th;
+  p.tiles_n = (d->n + p.tn - 1) / p.tn;
+  const int pixel_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  // ---- N tile
+  int BN = d->cout <= 256 ? ((d->cout + 15) / 16) * 16 : 256;
+  auto nblocks = [&](int bn) { return (d->cout + bn - 1) / bn; };
+  const int sms = sm_count();
+  while (BN >= 128 && BN % 32 == 0 && d->cout % (BN / 2) == 0 && pixel_tiles * nblocks(BN) < sms)
+    BN /= 2;
+  p.BN = BN;
+  p.acc_cols = (BN + 31) & ~31;
+  p.n_blocks = nblocks(BN);
+  p.total_tiles = pixel_tiles * p.n_blocks;
+  p.Nimg = d->n;
+  p.Ho = d->h_out;
+  p.Wo = d->w_out;
+  p.in_stride = d->in_stride;
+  p.in_off_y = d->in_off_y;
+  p.in_off_x = d->in_off_x;
+  p.cin_off = d->cin_off;
+  p.k_chunks = (d->cin + 63) / 64;
+  p.last_k16 = (d->cin % 64 == 0) ? 4 : (d->cin % 64) / 16;
+  p.ntaps = d->ntaps;
+  for (int t = 0; t < d->ntaps; ++t) {
+    p.tap_dy[t] = d->tap_dy[t];
+    p.tap_dx[t] = d->tap_dx[t];
+    p.tap_w[t] = d->tap_w[t];
+    B200_REQUIRE(d->tap_w[t] >= 0 && d->tap_w[t] < d->w_taps, "b200_conv_igemm: tap_w out of range");
+  }
+  p.Cout = d->cout;
+  p.b_bytes = (uint32_t)BN * 128;
+  p.stage_bytes = kABytes + ((p.b_bytes + 1023) & ~1023u);
+  p.stages = (kSmemBytes - 2048) / (int)p.stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  B200_REQUIRE(p.stages >= 2, "b200_conv_igemm: not enough shared memory for 2 stages");
+
+  // ---- tensor maps
+  {
+    uint64_t dims[4] = {(uint64_t)(d->cin_off + d->cin), (uint64_t)d->w_in, (uint64_t)d->h_in,
+                        (uint64_t)d->n};
+    uint64_t strides[3] = {(uint64_t)d->cx * 2, (uint64_t)d->w_in * d->cx * 2,
+                           (uint64_t)d->h_in * d->w_in * d->cx * 2};
+    uint32_t box[4] = {64, (uint32_t)(p.tw * d->in_stride), (uint32_t)(p.th * d->in_stride),
+                       (uint32_t)p.tn};
+    uint32_t es[4] = {1, (uint32_t)d->in_stride, (uint32_t)d->in_stride, 1};
+    if (make_tensor_map(&p.in_map, x, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)d->w_cin_pad, (uint64_t)d->w_cout_pad, (uint64_t)d->w_taps};
+    uint64_t strides[2] = {(uint64_t)d->w_cin_pad * 2, (uint64_t)d->w_cout_pad * d->w_cin_pad * 2};
+    uint32_t box[3] = {64, (uint32_t)BN, 1};
+    if (make_tensor_map(&p.w_map, w_packed, 3, dims, strides, box, nullptr,
+                        CU_TENSOR_MAP_SWIZZLE_128B))
+      return 1;
+  }
+  // ---- output placement
+  p.out = reinterpret_cast<__nv_bfloat16*>(y);
+  p.o_sx = d->cy;
+  p.o_sy = (long long)d->w_buf * d->cy;
+  p.o_sn = (long long)d->h_buf * d->w_buf * d->cy;
+  p.o_coff = d->cout_off;
+  p.upsample = d->upsample2x;
+  if (d->upsample2x) {
+    p.o_my = 2; p.o_oy = 0; p.o_mx = 2; p.o_ox = 0;
+    B200_REQUIRE(d->h_buf == 2 * d->h_out && d->w_buf == 2 * d->w_out, "b200_conv_igemm: upsample buffer dims");
+  } else {
+    p.o_my = d->out_mul_y ? d->out_mul_y : 1;
+    p.o_oy = d->out_off_y;
+    p.o_mx = d->out_mul_x ? d->out_mul_x : 1;
+    p.o_ox = d->out_off_x;
+    B200_REQUIRE((d->h_out - 1) * p.o_my + p.o_oy < d->h_buf && (d->w_out - 1) * p.o_mx + p.o_ox < d->w_buf,
+                 "b200_conv_igemm: output placement exceeds buffer");
+  }
+  if (d->upsample2x) {
+    p.aux_h = d->h_out; p.aux_w = d->w_out; p.aux_my = 1; p.aux_oy = 0; p.aux_mx = 1; p.aux_ox = 0;
+  } else {
+    p.aux_h = d->h_buf; p.aux_w = d->w_buf;
+    p.aux_my = p.o_my; p.aux_oy = p.o_oy; p.aux_mx = p.o_mx; p.aux_ox = p.o_ox;
+  }
+  p.bias = bias;
+  p.alpha = d->alpha;
+  p.act = d->act;
+  p.slope = d->slope;
+  p.res1 = reinterpret_cast<const __nv_bfloat16*>(res1);
+  p.res2 = reinterpret_cast<const __nv_bfloat16*>(res2);
+  p.res1_c = d->res1_c; p.res1_coff = d->res1_coff;
+  p.res2_c = d->res2_c; p.res2_coff = d->res2_coff;
+  p.res_nch = (res1 || res2) ? (d->res_nch > 0 ? d->res_nch : d->cout) : 0;
+  p.beta1 = d->beta1; p.beta2 = d->beta2;
+  p.accumulate = d->accumulate;
+  p.mask = reinterpret_cast<const __nv_bfloat16*>(mask);
+  p.mask_c = d->mask_c; p.mask_coff = d->mask_coff;
+  p.mask_lo = d->mask_lo; p.mask_hi = d->mask_hi;
+  p.mask_slope = d->mask_slope;
+
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  conv_igemm_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(p);
+  B200_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,343 @@
+// 3x3 stride-1 pad-1 convolutions with a thin (<= 4 channel, image) side: CUDA-core direct kernels.
+// K = 27 (or N = 3) is a degenerate GEMM for tcgen05, and these layers are HBM/LSU bound:
+//   RRDBNet fea_conv 3->64 and HR_conv1 64->3 (RRDBNet_arch.py:23,40), Discriminator_VGG conv0
+//   (discriminators.py:21), VGG19 conv1_1 with the ImageNet input normalisation folded in
+//   (perceptual.py:207,210) -- forward, input gradient and weight gradient.
+// The thin side is NCHW fp32 (the layout of images at the nn.Module boundary), the wide side is
+// NHWC bf16 (the internal activation layout).
+#include "common.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int kMaxThin = 4;
+
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+// ---------------------------------------------------------------- thin -> wide
+// block (32 x 8 pixels); dynamic smem: weights [cs*9][cw] fp32
+template <int CS>
+__global__ void __launch_bounds__(256)
+thin_to_wide_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
+                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int n, int h,
+                    int w, int cw, int cy, int y_coff, int transpose_w,
+                    const float* __restrict__ mean, const float* __restrict__ stdv, int act,
+                    float slope, const __nv_bfloat16* __restrict__ mask, int mask_c, int mask_coff,
+                    float mask_slope) {
+  extern __shared__ float wsm[];  // [CS*9][cw]
+  __shared__ float patch[CS][10][34];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < CS * 9 * cw; i += 256) {
+    const int j = i % cw;        // wide channel
+    const int it = i / cw;       // cs_i * 9 + t'
+    const int ci = it / 9, t = it % 9;
+    wsm[i] = transpose_w ? wgt[((size_t)ci * cw + j) * 9 + (8 - t)] : wgt[((size_t)j * CS + ci) * 9 + t];
+  }
+  const int tiles_x = (w + 31) / 32, tiles_y = (h + 7) / 8;
+  const int b = blockIdx.x / (tiles_x * tiles_y);
+  const int tr = blockIdx.x % (tiles_x * tiles_y);
+  const int x0 = (tr % tiles_x) * 32, y0 = (tr / tiles_x) * 8;
+  for (int i = tid; i < CS * 10 * 34; i += 256) {
+    const int px = i % 34, py = (i / 34) % 10, ci = i / 340;
+    const int gx = x0 + px - 1, gy = y0 + py - 1;
+    float v = 0.f;
+    if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+      v = x[(((size_t)b * CS + ci) * h + gy) * w + gx];
+      if (mean) v = (v - mean[ci]) / stdv[ci];
+    }
+    patch[ci][py][px] = v;
+  }
+  __syncthreads();
+  const int tx = tid & 31, ty = tid >> 5;
+  const int gx = x0 + tx, gy = y0 + ty;
+  if (gx >= w || gy >= h) return;
+  float pv[CS * 9];
+#pragma unroll
+  for (int ci = 0; ci < CS; ++ci)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) pv[ci * 9 + t] = patch[ci][ty + t / 3][tx + t % 3];
+  __nv_bfloat16* dst = y + (((size_t)b * h + gy) * w + gx) * cy + y_coff;
+  for (int g = 0; g < cw; g += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[g + j] : 0.f;
+#pragma unroll
+    for (int k = 0; k < CS * 9; ++k) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&wsm[k * cw + g]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&wsm[k * cw + g + 4]);
+      const float v = pv[k];
+      acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
+      acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+      acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+      acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+    }
+    if (act) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = acc[j] > 0.f ? acc[j] : acc[j] * slope;
+    }
+    if (mask) {
+      float mv[8];
+      unpack8(*reinterpret_cast<const uint4*>(mask + (((size_t)b * h + gy) * w + gx) * mask_c +
+                                              mask_coff + g),
+              mv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = mv[j] > 0.f ? acc[j] : acc[j] * mask_slope;
+    }
+    *reinterpret_cast<uint4*>(dst + g) = pack8(acc);
+  }
+}
+
+// ---------------------------------------------------------------- wide -> thin
+// block 16x16 pixels; dynamic smem: tile [18*18][cw] bf16 (16-byte chunks XOR-swizzled by pixel) +
+// weights [9][cw][4] fp32
+__global__ void __launch_bounds__(256)
+wide_to_thin_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wgt,
+                    const float* __restrict__ bias, float* __restrict__ y, int n, int h, int w, int cw,
+                    int cx, int x_coff, int cs, int transpose_w, const float* __restrict__ inv_std,
+                    float out_scale) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  const int chunks = cw / 8;
+  uint4* tile = reinterpret_cast<uint4*>(dsm);                       // [324][chunks]
+  float4* wsm = reinterpret_cast<float4*>(dsm + (size_t)324 * chunks * 16);  // [9][cw]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 9 * cw; i += 256) {
+    const int j = i % cw, t = i / cw;
+    float wv[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ci = 0; ci < cs; ++ci)
+      wv[ci] = transpose_w ? wgt[((size_t)j * cs + ci) * 9 + (8 - t)] : wgt[((size_t)ci * cw + j) * 9 + t];
+    wsm[i] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+  }
+  const int tiles_x = (w + 15) / 16, tiles_y = (h + 15) / 16;
+  const int b = blockIdx.x / (tiles_x * tiles_y);
+  const int tr = blockIdx.x % (tiles_x * tiles_y);
+  const int x0 = (tr % tiles_x) * 16, y0 = (tr / tiles_x) * 16;
+  const int swz_mask = chunks >= 8 ? 7 : (chunks - 1);
+  for (int i = tid; i < 324 * chunks; i += 256) {
+    const int ch = i % chunks, pix = i / chunks;
+    const int px = pix % 18, py = pix / 18;
+    const int gx = x0 + px - 1, gy = y0 + py - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (gx >= 0 && gx < w && gy >= 0 && gy < h)
+      v = *reinterpret_cast<const uint4*>(x + (((size_t)b * h + gy) * w + gx) * cx + x_coff + ch * 8);
+    tile[pix * chunks + (ch ^ (px & swz_mask))] = v;
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  const int gx = x0 + tx, gy = y0 + ty;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int t = 0; t < 9; ++t) {
+    const int px = tx + t % 3, py = ty + t / 3;
+    const int pix = py * 18 + px;
+    for (int ch = 0; ch < chunks; ++ch) {
+      float f[8];
+      unpack8(tile[pix * chunks + (ch ^ (px & swz_mask))], f);
+      const float4* wp = wsm + t * cw + ch * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 wv = wp[k];
+        acc[0] = fmaf(f[k], wv.x, acc[0]);
+        acc[1] = fmaf(f[k], wv.y, acc[1]);
+        acc[2] = fmaf(f[k], wv.z, acc[2]);
+        acc[3] = fmaf(f[k], wv.w, acc[3]);
+      }
+    }
+  }
+  if (gx >= w || gy >= h) return;
+  for (int co = 0; co < cs; ++co) {
+    float v = acc[co] + (bias ? bias[co] : 0.f);
+    if (inv_std) v *= inv_std[co];
+    y[(((size_t)b * cs + co) * h + gy) * w + gx] = v * out_scale;
+  }
+}
+
+// ---------------------------------------------------------------- weight gradient
+// acc[j (wide)][i (thin)][t] = sum_p wide[p, j] * thin[p + sign * off_t, i]
+// block = 64 wide-channel lanes x 4 pixel subsets; one image row per iteration.
+template <int CS>
+__global__ void __launch_bounds__(256)
+thin_wgrad_kernel(const float* __restrict__ thin, const __nv_bfloat16* __restrict__ wide,
+                  float* __restrict__ dw, float* __restrict__ dbias_wide, int n, int h, int w,
+                  int cw, int cwide_buf, int wide_coff, int wide_is_out) {
+  extern __shared__ float rows[];  // [CS][3][w + 2]
+  __shared__ float red[4][64];
+  const int tid = threadIdx.x;
+  const int lane_c = tid & 63, sub = tid >> 6;
+  const int j = blockIdx.y * 64 + lane_c;
+  const int sign = wide_is_out ? 1 : -1;
+  const int wp = w + 2;
+  float acc[CS * 9];
+#pragma unroll
+  for (int k = 0; k < CS * 9; ++k) acc[k] = 0.f;
+  float bsum = 0.f;
+  const int total_rows = n * h;
+  for (int row = blockIdx.x; row < total_rows; row += gridDim.x) {
+    const int b = row / h, yy = row % h;
+    __syncthreads();
+    for (int i = tid; i < CS * 3 * wp; i += 256) {
+      const int px = i % wp, r = (i / wp) % 3, ci = i / (3 * wp);
+      const int gy = yy + (r - 1), gx = px - 1;
+      float v = 0.f;
+      if (gx >= 0 && gx < w && gy >= 0 && gy < h) v = thin[(((size_t)b * CS + ci) * h + gy) * w + gx];
+      rows[i] = v;
+    }
+    __syncthreads();
+    if (j < cw) {
+      const __nv_bfloat16* wrow = wide + ((size_t)b * h + yy) * w * cwide_buf + wide_coff + j;
+      for (int xx = sub; xx < w; xx += 4) {
+        const float v = __bfloat162float(wrow[(size_t)xx * cwide_buf]);
+        bsum += v;
+#pragma unroll
+        for (int ci = 0; ci < CS; ++ci)
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int dy = sign * (t / 3 - 1), dx = sign * (t % 3 - 1);
+            acc[ci * 9 + t] = fmaf(v, rows[(ci * 3 + 1 + dy) * wp + xx + 1 + dx], acc[ci * 9 + t]);
+          }
+      }
+    }
+  }
+  // reduce the 4 pixel subsets, then one atomic per (j, i, t)
+#pragma unroll
+  for (int k = 0; k < CS * 9 + 1; ++k) {
+    __syncthreads();
+    red[sub][lane_c] = (k < CS * 9) ? acc[k] : bsum;
+    __syncthreads();
+    if (sub == 0 && j < cw) {
+      const float s = red[0][lane_c] + red[1][lane_c] + red[2][lane_c] + red[3][lane_c];
+      if (k < CS * 9) {
+        const int ci = k / 9, t = k % 9;
+        const size_t idx = wide_is_out ? ((size_t)j * CS + ci) * 9 + t : ((size_t)ci * cw + j) * 9 + t;
+        atomicAdd(dw + idx, s);
+      } else if (dbias_wide) {
+        atomicAdd(dbias_wide + j, s);
+      }
+    }
+  }
+}
+
+__global__ void plane_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int n, int c,
+                                 long long hw) {
+  const int ch = blockIdx.y;
+  float s = 0.f;
+  for (int b = 0; b < n; ++b) {
+    const float* p = x + ((size_t)b * c + ch) * hw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hw;
+         i += (long long)gridDim.x * blockDim.x)
+      s += p[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    atomicAdd(out + ch, t);
+  }
+}
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+typedef __nv_bfloat16 bf16;
+
+extern "C" {
+
+int b200_conv3x3_thin_to_wide(const float* x, const float* w_oihw, const float* bias, void* y,
+                              int32_t n, int32_t h, int32_t w, int32_t cs, int32_t cw, int32_t cy,
+                              int32_t y_coff, int32_t transpose_w, const float* mean,
+                              const float* stdv, int32_t act, float slope, const void* mask,
+                              int32_t mask_c, int32_t mask_coff, float mask_slope,
+                              b200_stream_t stream) {
+  B200_REQUIRE(cs >= 1 && cs <= kMaxThin, "thin_to_wide: thin channels %d not in 1..4", cs);
+  B200_REQUIRE(cw % 8 == 0 && cy % 8 == 0 && y_coff % 8 == 0, "thin_to_wide: wide channels must be multiples of 8");
+  const int blocks = n * ((w + 31) / 32) * ((h + 7) / 8);
+  const size_t smem = (size_t)cs * 9 * cw * sizeof(float);
+  B200_REQUIRE(smem <= 40 * 1024, "thin_to_wide: cw too large");
+#define LAUNCH_TW(CS)                                                                            \
+  thin_to_wide_kernel<CS><<<blocks, 256, smem, as_stream(stream)>>>(                             \
+      x, w_oihw, bias, (bf16*)y, n, h, w, cw, cy, y_coff, transpose_w, mean, stdv, act, slope, \
+      (const bf16*)mask, mask_c, mask_coff, mask_slope)
+  switch (cs) {
+    case 1: LAUNCH_TW(1); break;
+    case 2: LAUNCH_TW(2); break;
+    case 3: LAUNCH_TW(3); break;
+    default: LAUNCH_TW(4); break;
+  }
+#undef LAUNCH_TW
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200_conv3x3_wide_to_thin(const void* x, const float* w_oihw, const float* bias, float* y,
+                              int32_t n, int32_t h, int32_t w, int32_t cw, int32_t cx, int32_t x_coff,
+                              int32_t cs, int32_t transpose_w, const float* inv_std, float out_scale,
+                              b200_stream_t stream) {
+  B200_REQUIRE(cs >= 1 && cs <= kMaxThin, "wide_to_thin: thin channels %d not in 1..4", cs);
+  B200_REQUIRE(cw % 8 == 0 && cx % 8 == 0 && x_coff % 8 == 0 && cw <= 128,
+               "wide_to_thin: wide channels must be multiples of 8 and <= 128");
+  const int chunks = cw / 8;
+  B200_REQUIRE((chunks & (chunks - 1)) == 0, "wide_to_thin: cw/8 must be a power of two");
+  const size_t smem = (size_t)324 * chunks * 16 + (size_t)9 * cw * 16;
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(wide_to_thin_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const int blocks = n * ((w + 15) / 16) * ((h + 15) / 16);
+  wide_to_thin_kernel<<<blocks, 256, smem, as_stream(stream)>>>(
+      (const bf16*)x, w_oihw, bias, y, n, h, w, cw, cx, x_coff, cs, transpose_w, inv_std, out_scale);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200_conv3x3_thin_wgrad(const float* thin, const void* wide, float* dw, float* dbias_wide,
+                            float* dbias_thin, int32_t n, int32_t h, int32_t w, int32_t cs,
+                            int32_t cw, int32_t cwide_buf, int32_t wide_coff, int32_t wide_is_out,
+                            const float* mean, const float* stdv, b200_stream_t stream) {
+  (void)mean;
+  (void)stdv;
+  B200_REQUIRE(cs >= 1 && cs <= kMaxThin, "thin_wgrad: thin channels %d not in 1..4", cs);
+  const size_t smem = (size_t)cs * 3 * (w + 2) * sizeof(float);
+  B200_REQUIRE(smem <= 48 * 1024, "thin_wgrad: row too wide");
+  int gx = n * h < 2 * sm_count() ? n * h : 2 * sm_count();
+  dim3 grid(gx, (cw + 63) / 64);
+#define LAUNCH_WG(CS)                                                               \
+  thin_wgrad_kernel<CS><<<grid, 256, smem, as_stream(stream)>>>(                    \
+      thin, (const bf16*)wide, dw, dbias_wide, n, h, w, cw, cwide_buf, wide_coff, wide_is_out)
+  switch (cs) {
+    case 1: LAUNCH_WG(1); break;
+    case 2: LAUNCH_WG(2); break;
+    case 3: LAUNCH_WG(3); break;
+    default: LAUNCH_WG(4); break;
+  }
+#undef LAUNCH_WG
+  B200_LAUNCH_CHECK();
+  if (dbias_thin) {
+    dim3 g2(32, cs);
+    plane_sum_kernel<<<g2, 256, 0, as_stream(stream)>>>(thin, dbias_thin, n, cs, (long long)h * w);
+    B200_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // extern "C"

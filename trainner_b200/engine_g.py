@@ -1,0 +1,234 @@
+"""Fused forward/backward engine of the RRDBNet generator (reference: RRDBNet_arch.py:14-163).
+
+HBM layout: every RDB owns ONE NHWC bf16 buffer [N, h, w, nf + 4*gc]; conv_k reads channels
+[0, nf+(k-1)gc) and writes its LeakyReLU'd output into channels [nf+(k-1)gc, nf+k*gc) -- the
+reference's four torch.cat copies per RDB do not exist.  conv5's epilogue writes
+0.2*conv5 + x (and, for the third RDB of an RRDB, the RRDB residual too) straight into channels
+[0, nf) of the NEXT RDB's buffer.  The buffers double as the saved activations for backward; the
+LeakyReLU masks are recomputed from the sign of the stored outputs.
+
+Backward keeps one gradient buffer per RDB (ring of 4): dgrad of conv_k accumulates into channels
+[0, nf+(k-1)gc) in the epilogue (read-modify-write), and the LAST writer of a slice applies that
+slice's LeakyReLU mask, so the slice is directly conv_{k-1}'s pre-activation gradient.
+"""
+import torch
+
+from . import _lib
+from ._lib import lib
+from .runtime import (ConvLayer, ContextPool, FlatGrads, Lease, LRELU_SLOPE, P, Plan, WeightPacker,
+                      add_igemm, add_wgrad, make_conv_desc, require_device, taps_conv, taps_dgrad_s1)
+
+BF16 = torch.bfloat16
+
+
+class _GContext:
+    pass
+
+
+class RRDBNetEngine:
+    def __init__(self, net):
+        self.net = net
+        self.device = None
+        self.pools = {}
+
+    # ------------------------------------------------------------------ setup
+    def _setup(self, device):
+        net = self.net
+        self.device = device
+        k = net._conv_index()
+        self.fea = k["fea"]
+        self.hr1 = k["hr1"]
+        self.rdbs = [[ConvLayer(c, "rdb%d.conv%d" % (i, j + 1)) for j, c in enumerate(convs)]
+                     for i, convs in enumerate(k["rdbs"])]
+        self.lr = ConvLayer(k["lr"], "LR_conv")
+        self.ups = [ConvLayer(c, "upconv%d" % i) for i, c in enumerate(k["ups"])]
+        self.hr0 = ConvLayer(k["hr0"], "HR_conv0")
+        self.tc_layers = [l for r in self.rdbs for l in r] + [self.lr] + self.ups + [self.hr0]
+        self.packer = WeightPacker(self.tc_layers, device)
+        self.grads = FlatGrads(list(net.parameters()), device)
+        self.pools = {}
+
+    def _ensure(self, x):
+        require_device(x, "RRDBNet")
+        if self.device != x.device or self.packer.stale_pointers():
+            self._setup(x.device)
+
+    # ------------------------------------------------------------------ plans
+    def _make_context(self, N, h, w):
+        net = self.net
+        nf, gc, S = net.nf, net.gc, net.upscale
+        C = nf + 4 * gc
+        dev = self.device
+        nrdb = len(self.rdbs)
+        ctx = _GContext()
+        ctx.shape = (N, h, w)
+        e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)
+        ctx.x = torch.empty(N, net.in_nc, h, w, dtype=torch.float32, device=dev)
+        ctx.B = [e(N, h, w, C) for _ in range(nrdb)] + [e(N, h, w, nf)]
+        Bc = [C] * nrdb + [nf]
+        # upsampler chain: U[i] is the (already nearest-upsampled) input of upconv i
+        ctx.U = []
+        hh, ww = h, w
+        for _ in self.ups:
+            hh, ww = hh * 2, ww * 2
+            ctx.U.append(e(N, hh, ww, nf))
+        H, W = hh, ww
+        ctx.V = e(N, H, W, nf)    # output of the last upconv (or of LR_conv when there is none)
+        ctx.Wt = e(N, H, W, nf)   # output of HR_conv0
+        ctx.out = torch.empty(N, net.out_nc, H, W, dtype=torch.float32, device=dev)
+        ctx.HW = (H, W)
+
+        # ---------------- forward plan
+        f = Plan()
+        f.add(lib.b200_conv3x3_thin_to_wide, P(ctx.x), P(self.fea.weight), P(self.fea.bias), P(ctx.B[0]),
+              N, h, w, net.in_nc, nf, Bc[0], 0, 0, None, None, 0, 0.0, None, 0, 0, 0.0)
+        for r, convs in enumerate(self.rdbs):
+            Bi, Bo = ctx.B[r], ctx.B[r + 1]
+            for kk in range(4):
+                L = convs[kk]
+                cin = nf + kk * gc
+                d = make_conv_desc(N, h, w, C, 0, cin, h, w, h, w, C, cin, gc, taps_conv(3, 1), L.taps,
+                                   L.fwd_rows, L.fwd_cols, act=1, slope=LRELU_SLOPE)
+                add_igemm(f, d, Bi, L.w_fwd, L.bias, y=Bi)
+            L = convs[4]
+            last_of_rrdb = (r % 3 == 2)
+            a = 0.04 if last_of_rrdb else 0.2
+            b1 = 0.2 if last_of_rrdb else 1.0
+            d = make_conv_desc(N, h, w, C, 0, C, h, w, h, w, Bc[r + 1], 0, nf, taps_conv(3, 1), L.taps,
+                               L.fwd_rows, L.fwd_cols, alpha=a, beta1=b1, res_nch=nf, res1_c=C,
+                               res1_coff=0, beta2=1.0 if last_of_rrdb else 0.0, res2_c=C, res2_coff=0)
+            add_igemm(f, d, Bi, L.w_fwd, L.bias, res1=Bi, res2=ctx.B[r - 2] if last_of_rrdb else None, y=Bo)
+        # LR_conv + shortcut (+ nearest x2 folded into the store when an upconv follows)
+        L = self.lr
+        first_dst = ctx.U[0] if self.ups else ctx.V
+        hb, wb = (2 * h, 2 * w) if self.ups else (h, w)
+        d = make_conv_desc(N, h, w, nf, 0, nf, h, w, hb, wb, nf, 0, nf, taps_conv(3, 1), L.taps, L.fwd_rows,
+                           L.fwd_cols, upsample=1 if self.ups else 0, beta1=1.0, res_nch=nf, res1_c=Bc[0],
+                           res1_coff=0)
+        add_igemm(f, d, ctx.B[nrdb], L.w_fwd, L.bias, res1=ctx.B[0], y=first_dst)
+        hh, ww = h, w
+        for i, L in enumerate(self.ups):
+            hh, ww = hh * 2, ww * 2
+            lastu = (i == len(self.ups) - 1)
+            dst = ctx.V if lastu else ctx.U[i + 1]
+            d = make_conv_desc(N, hh, ww, nf, 0, nf, hh, ww, hh if lastu else 2 * hh, ww if lastu else 2 * ww,
+                               nf, 0, nf, taps_conv(3, 1), L.taps, L.fwd_rows, L.fwd_cols,
+                               upsample=0 if lastu else 1, act=1, slope=LRELU_SLOPE)
+            add_igemm(f, d, ctx.U[i], L.w_fwd, L.bias, y=dst)
+        L = self.hr0
+        d = make_conv_desc(N, H, W, nf, 0, nf, H, W, H, W, nf, 0, nf, taps_conv(3, 1), L.taps, L.fwd_rows,
+                           L.fwd_cols, act=1, slope=LRELU_SLOPE)
+        add_igemm(f, d, ctx.V, L.w_fwd, L.bias, y=ctx.Wt)
+        f.add(lib.b200_conv3x3_wide_to_thin, P(ctx.Wt), P(self.hr1.weight), P(self.hr1.bias), P(ctx.out),
+              N, H, W, nf, nf, 0, net.out_nc, 0, None, 1.0)
+        ctx.fwd = f
+        ctx.bwd = None
+        return ctx
+
+    def _make_backward(self, ctx):
+        net = self.net
+        nf, gc = net.nf, net.gc
+        C = nf + 4 * gc
+        N, h, w = ctx.shape
+        H, W = ctx.HW
+        dev = self.device
+        nrdb = len(self.rdbs)
+        g = self.grads.view
+        e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)
+        ctx.dout = torch.empty(N, net.out_nc, H, W, dtype=torch.float32, device=dev)
+        ctx.dWt = e(N, H, W, nf)
+        ctx.dV = e(N, H, W, nf)
+        ctx.dU = [e(*u.shape) for u in ctx.U]
+        ctx.dP = [e(u.shape[0], u.shape[1] // 2, u.shape[2] // 2, nf) for u in ctx.U]
+        ctx.G = [e(N, h, w, C) for _ in range(4)]
+        b = Plan()
+        SL = LRELU_SLOPE
+        # HR_conv1 (wide->thin) backward
+        b.add(lib.b200_conv3x3_thin_to_wide, P(ctx.dout), P(self.hr1.weight), None, P(ctx.dWt), N, H, W,
+              net.out_nc, nf, nf, 0, 1, None, None, 0, 0.0, P(ctx.Wt), nf, 0, SL)
+        b.add(lib.b200_conv3x3_thin_wgrad, P(ctx.dout), P(ctx.Wt), P(g(self.hr1.weight)), None,
+              P(g(self.hr1.bias)), N, H, W, net.out_nc, nf, nf, 0, 0, None, None)
+        # HR_conv0
+        L = self.hr0
+        d = make_conv_desc(N, H, W, nf, 0, nf, H, W, H, W, nf, 0, nf, taps_dgrad_s1(3, 1), L.taps, L.dgr_rows,
+                           L.dgr_cols, mask_c=nf, mask_coff=0, mask_lo=0, mask_hi=nf, mask_slope=SL)
+        add_igemm(b, d, ctx.dWt, L.w_dgr, mask=ctx.V, y=ctx.dV)
+        add_wgrad(b, N, H, W, nf, 0, nf, H, W, nf, 0, nf, 3, 1, 1, 1.0, ctx.V, ctx.dWt, g(L.weight), g(L.bias))
+        # upconvs, last to first.  dcur = gradient wrt the pre-activation of upconv i's conv output
+        dcur = ctx.dV
+        hh, ww = H, W
+        for i in range(len(self.ups) - 1, -1, -1):
+            L = self.ups[i]
+            d = make_conv_desc(N, hh, ww, nf, 0, nf, hh, ww, hh, ww, nf, 0, nf, taps_dgrad_s1(3, 1), L.taps,
+                               L.dgr_rows, L.dgr_cols)
+            add_igemm(b, d, dcur, L.w_dgr, y=ctx.dU[i])
+            add_wgrad(b, N, hh, ww, nf, 0, nf, hh, ww, nf, 0, nf, 3, 1, 1, 1.0, ctx.U[i], dcur, g(L.weight),
+                      g(L.bias))
+            hh, ww = hh // 2, ww // 2
+            # undo the nearest upsample; U[i] = up(lrelu(conv_{i-1})) for i > 0 carries the mask
+            b.add(lib.b200_sumpool2x2_mask, P(ctx.dU[i]), P(ctx.U[i]) if i > 0 else None, P(ctx.dP[i]), N, hh,
+                  ww, nf, SL)
+            dcur = ctx.dP[i]
+        dT = dcur  # gradient wrt (fea + LR_conv(trunk)) at LR resolution
+        slot = lambda r: ctx.G[r % 4]
+        L = self.lr
+        d = make_conv_desc(N, h, w, nf, 0, nf, h, w, h, w, C, 0, nf, taps_dgrad_s1(3, 1), L.taps, L.dgr_rows,
+                           L.dgr_cols)
+        add_igemm(b, d, dT, L.w_dgr, y=slot(nrdb))
+        add_wgrad(b, N, h, w, nf, 0, nf, h, w, nf, 0, nf, 3, 1, 1, 1.0, ctx.B[nrdb], dT, g(L.weight), g(L.bias))
+        for r in range(nrdb - 1, -1, -1):
+            convs = self.rdbs[r]
+            Gr, dO, Br = slot(r), slot(r + 1), ctx.B[r]
+            last_of_rrdb = (r % 3 == 2)
+            first_of_rrdb = (r % 3 == 0)
+            a = 0.04 if last_of_rrdb else 0.2
+            b1 = 0.2 if last_of_rrdb else 1.0
+            L = convs[4]
+            d = make_conv_desc(N, h, w, C, 0, nf, h, w, h, w, C, 0, C, taps_dgrad_s1(3, 1), L.taps, L.dgr_rows,
+                               L.dgr_cols, alpha=a, beta1=b1, res_nch=nf, res1_c=C, res1_coff=0,
+                               beta2=1.0 if first_of_rrdb else 0.0, res2_c=C, res2_coff=0, mask_c=C,
+                               mask_coff=0, mask_lo=nf + 3 * gc, mask_hi=C, mask_slope=SL)
+            add_igemm(b, d, dO, L.w_dgr, res1=dO, res2=slot(r + 3) if first_of_rrdb else None, mask=Br, y=Gr)
+            add_wgrad(b, N, h, w, C, 0, C, h, w, C, 0, nf, 3, 1, 1, a, Br, dO, g(L.weight), g(L.bias))
+            for kk in range(3, -1, -1):
+                L = convs[kk]
+                lo = nf + kk * gc  # this conv's output slice [lo, lo+gc) == its dY; inputs are [0, lo)
+                d = make_conv_desc(N, h, w, C, lo, gc, h, w, h, w, C, 0, lo, taps_dgrad_s1(3, 1), L.taps,
+                                   L.dgr_rows, L.dgr_cols, accumulate=1, mask_c=C, mask_coff=0,
+                                   mask_lo=lo - gc if kk > 0 else 0, mask_hi=lo if kk > 0 else 0,
+                                   mask_slope=SL)
+                add_igemm(b, d, Gr, L.w_dgr, mask=Br if kk > 0 else None, y=Gr)
+                add_wgrad(b, N, h, w, C, 0, lo, h, w, C, lo, gc, 3, 1, 1, 1.0, Br, Gr, g(L.weight), g(L.bias))
+        # shortcut: d(fea) = G[0][0:nf] + dT
+        G0 = slot(0)
+        b.add(lib.b200_add_slice_bf16, P(G0), C, 0, P(dT), nf, 0, N * h * w, nf)
+        b.add(lib.b200_conv3x3_thin_wgrad, P(ctx.x), P(G0), P(g(self.fea.weight)), P(g(self.fea.bias)), None,
+              N, h, w, net.in_nc, nf, C, 0, 1, None, None)
+        ctx.bwd = b
+
+    # ------------------------------------------------------------------ run
+    def forward(self, x, need_backward):
+        self._ensure(x)
+        N, _, h, w = x.shape
+        key = (N, h, w)
+        if key not in self.pools:
+            self.pools[key] = ContextPool(lambda: self._make_context(N, h, w))
+        pool = self.pools[key]
+        ctx = pool.acquire()
+        self.packer.ensure()
+        ctx.x.copy_(x)
+        ctx.fwd.run()
+        out = ctx.out.clone()
+        if need_backward:
+            return out, Lease(pool, ctx)
+        pool.release(ctx)
+        return out, None
+
+    def backward(self, lease, dout):
+        ctx = lease.ctx
+        if ctx.bwd is None:
+            self._make_backward(ctx)
+        self.grads.attach()
+        ctx.dout.copy_(dout)
+        ctx.bwd.run()
+        lease.release()
