@@ -38,10 +38,12 @@ class Plan:
 
     def __init__(self):
         self.calls = []
+        self.meta = []   # (kernel tag, algorithmic FLOPs) per call, for the roofline report
         self._keep = []
 
-    def add(self, fn, *args):
+    def add(self, fn, *args, flops=0.0, tag=None):
         self.calls.append((fn, args))
+        self.meta.append((tag or fn.__name__, float(flops)))
 
     def keep(self, obj):
         self._keep.append(obj)
@@ -53,6 +55,22 @@ class Plan:
             if fn(*args, s):
                 raise RuntimeError("trainner_b200 kernel call %s failed: %s" %
                                    (fn.__name__, lib.b200_last_error().decode()))
+
+    def run_timed(self):
+        """Run with a CUDA event pair around every call (on the launching stream); returns
+        [(tag, milliseconds, flops)].  Used by bench.py's roofline leg, never in the timed step."""
+        s = stream_ptr()
+        evs = []
+        for fn, args in self.calls:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if fn(*args, s):
+                raise RuntimeError("trainner_b200 kernel call %s failed: %s" %
+                                   (fn.__name__, lib.b200_last_error().decode()))
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return [(m[0], e0.elapsed_time(e1), m[1]) for m, (e0, e1) in zip(self.meta, evs)]
 
     def __len__(self):
         return len(self.calls)
@@ -255,7 +273,9 @@ def make_conv_desc(n, h_in, w_in, cx, cin_off, cin, h_out, w_out, h_buf, w_buf, 
 
 def add_igemm(plan, desc, x, w, bias=None, res1=None, res2=None, mask=None, y=None):
     plan.keep(desc)
-    plan.add(lib.b200_conv_igemm, C.byref(desc), P(x), P(w), P(bias), P(res1), P(res2), P(mask), P(y))
+    flops = 2.0 * desc.n * desc.h_out * desc.w_out * desc.cout * desc.cin * desc.ntaps
+    plan.add(lib.b200_conv_igemm, C.byref(desc), P(x), P(w), P(bias), P(res1), P(res2), P(mask), P(y),
+             flops=flops, tag="conv_igemm")
 
 
 def add_wgrad(plan, n, h_in, w_in, cx, x_coff, cin, h_out, w_out, cdy, dy_coff, cout, k, stride, pad,
@@ -263,4 +283,5 @@ def add_wgrad(plan, n, h_in, w_in, cx, x_coff, cin, h_out, w_out, cdy, dy_coff, 
     d = WgradDesc(n, h_in, w_in, cx, x_coff, cin, h_out, w_out, cdy, dy_coff, cout, k, k, stride, pad,
                   scale)
     plan.keep(d)
-    plan.add(lib.b200_conv_wgrad, C.byref(d), P(x), P(dy), P(dw), P(db))
+    plan.add(lib.b200_conv_wgrad, C.byref(d), P(x), P(dy), P(dw), P(db),
+             flops=2.0 * n * h_out * w_out * cout * cin * k * k, tag="conv_wgrad")
