@@ -68,7 +68,7 @@ class _RRDBNetFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, anchor, engine):
-        need_bwd = torch.is_grad_enabled() and (x.requires_grad or anchor.requires_grad)
+        need_bwd = any(ctx.needs_input_grad)  # (autograd runs forward() with grad mode off)
         out, lease = engine.forward(x, need_bwd)
         ctx.engine, ctx.lease = engine, lease
         return out

@@ -16,9 +16,9 @@ from ..engine_d import DiscriminatorEngine
 class _DFeaturesFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, anchor, engine, training):
-        need_bwd = torch.is_grad_enabled() and (x.requires_grad or anchor.requires_grad)
+        need_bwd = any(ctx.needs_input_grad)  # (autograd runs forward() with grad mode off)
         feat, lease = engine.forward(x, need_bwd, training)
-        ctx.engine, ctx.lease, ctx.xgrad = engine, lease, x.requires_grad
+        ctx.engine, ctx.lease, ctx.xgrad = engine, lease, ctx.needs_input_grad[0]
         return feat
 
     @staticmethod

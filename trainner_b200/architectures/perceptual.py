@@ -31,7 +31,7 @@ def vgg_layer_names(net):
 class _FeatureFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, engine, listen):
-        need_bwd = torch.is_grad_enabled() and x.requires_grad
+        need_bwd = any(ctx.needs_input_grad)  # (autograd runs forward() with grad mode off)
         outs, lease = engine.forward(x, need_bwd, listen)
         ctx.engine, ctx.lease, ctx.listen = engine, lease, listen
         # logical NCHW view of the NHWC storage (zero-copy, channels_last strides)

@@ -74,6 +74,18 @@ class SRModel:
         self.exchange.broadcast_params([self.netG] + ([self.netD] if self.netD is not None else []))
         self.optGstep = self.optDstep = False
 
+    @staticmethod
+    def _engines(net):
+        return [m._engine[0] for m in net.modules() if getattr(m, "_engine", None)]
+
+    def _mark_dirty(self, net):
+        """This model owns the optimizers: weights are repacked once per optimizer step instead of
+        at every forward (D runs 4 forwards per iteration)."""
+        for e in self._engines(net):
+            if getattr(e, "packer", None) is not None:
+                e.packer.explicit = True
+                e.packer.mark_dirty()
+
     # ------------------------------------------------------------------ reference-facing API
     def feed_data(self, data, need_HR=True):
         """sr_model.py:115-128: H2D of LR (+HR, ref)."""
@@ -113,6 +125,7 @@ class SRModel:
             self.exchange.all_reduce_grads(net)
             optimizer.step()
             optimizer.zero_grad()
+            self._mark_dirty(net)
             if opt_flag == "G":
                 self.optGstep = True
             else:

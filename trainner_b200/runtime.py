@@ -139,19 +139,34 @@ class WeightPacker:
             self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
             self.max_elems = max(e.taps * e.rows_pad * e.cols_pad for e in entries)
         self.version = None
+        self.dirty = True
+        self.explicit = False
+        self.was_trainable = False
         self.ptr_sig = tuple(l.weight.data_ptr() for l in layers)
 
     def stale_pointers(self):
         return self.ptr_sig != tuple(l.weight.data_ptr() for l in self.layers)
 
+    def mark_dirty(self):
+        self.dirty = True
+
     def ensure(self):
+        """Repack before a forward.  Parameter updates are NOT reliably visible through
+        Tensor._version (fused optimizers mutate through tensor lists), so by default every forward
+        of a trainable network repacks (one ~20 us launch).  A caller that owns the optimizer can
+        switch to explicit mode (`explicit = True`) and call mark_dirty() after each step; frozen
+        networks repack only when their tensors are replaced or versions change."""
         if not self.count:
             return
         ver = sum(l.weight._version for l in self.layers)
-        if ver != self.version:
+        trainable = any(l.weight.requires_grad for l in self.layers) or self.was_trainable
+        self.was_trainable = self.was_trainable or trainable
+        need = self.dirty or ver != self.version or (trainable and not self.explicit)
+        if need:
             _lib.check(lib.b200_pack_weights(self.table.data_ptr(), self.count, self.max_elems,
                                              stream_ptr()), "pack_weights")
             self.version = ver
+            self.dirty = False
 
 
 class FlatGrads:
