@@ -153,7 +153,8 @@ def cpu_reference_steps(args, steps, warmup, threads=None):
     import torchvision
     from trainner_b200 import networks
     from trainner_b200.architectures import discriminators, RRDBNet_arch
-    torch.set_num_threads(threads or os.cpu_count())
+    # oneDNN convolutions at batch 1 stop scaling (and oversubscribe badly) past a few dozen threads
+    torch.set_num_threads(threads or min(os.cpu_count(), 32))
     torch.manual_seed(0)
     g = RRDBNet_arch.RRDBNet(3, 3, 64, args.nb)
     networks.init_weights(g, "kaiming", 0.1)
@@ -291,10 +292,21 @@ def main():
             rows.extend(self.run_timed())
 
         runtime.Plan.run = timed_run
+        detail = [] if os.environ.get("B200_BENCH_DETAIL") else None
+        runtime.Plan.detail_sink = detail
         try:
             step_resident()
         finally:
             runtime.Plan.run = orig_run
+            runtime.Plan.detail_sink = None
+        if detail is not None:
+            grp = {}
+            for tag, info, t_ms, fl in detail:
+                a = grp.setdefault((tag, info), [0, 0.0, 0.0])
+                a[0] += 1; a[1] += t_ms; a[2] += fl
+            with open(os.environ["B200_BENCH_DETAIL"], "w") as fh:
+                for (tag, info), (c, t, fl) in sorted(grp.items(), key=lambda kv: -kv[1][1]):
+                    fh.write("%-26s %-44s n=%4d  %8.3f ms  %7.1f TF/s\n" % (tag, info, c, t, fl / (t * 1e-3) / 1e12 if t > 0 else 0))
         torch.cuda.synchronize()
         agg = {}
         for tag, t_ms, fl in rows:
@@ -317,9 +329,9 @@ def main():
                 "step_algorithmic_tflops": GFLOP_PER_IMAGE_STEP * 1e-3 * args.batch,
                 "step_frac_of_peak": (GFLOP_PER_IMAGE_STEP * 1e9 * (args.batch / (ms / 1e3))) / (peak * 1e12)}
         if not args.no_cpu_baseline and world == 1:
-            c_ips, c_dt, threads = cpu_reference_steps(args, 3, 1)
+            c_ips, c_dt, threads = cpu_reference_steps(args, 2, 1)
             cpu_base = {"value": c_ips * px, "unit": "HR-px/s", "images_per_sec": c_ips, "cores": threads,
-                        "kind": "port", "sample": "3 timed steps at batch 1 (nb=%d, HR %d^2), fp32" % (args.nb, args.hr)}
+                        "kind": "port", "sample": "2 timed steps at batch 1 (nb=%d, HR %d^2), fp32" % (args.nb, args.hr)}
     if world > 1:
         dist.barrier()
     if rank == 0:

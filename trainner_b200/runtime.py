@@ -36,14 +36,16 @@ def roundup(v, m):
 class Plan:
     """A list of (C function, argument tuple); the stream is appended at run time."""
 
+    detail_sink = None  # set to a list to collect (tag, info, ms, flops) per call from run_timed()
+
     def __init__(self):
         self.calls = []
         self.meta = []   # (kernel tag, algorithmic FLOPs) per call, for the roofline report
         self._keep = []
 
-    def add(self, fn, *args, flops=0.0, tag=None):
+    def add(self, fn, *args, flops=0.0, tag=None, info=""):
         self.calls.append((fn, args))
-        self.meta.append((tag or fn.__name__, float(flops)))
+        self.meta.append((tag or fn.__name__, float(flops), info))
 
     def keep(self, obj):
         self._keep.append(obj)
@@ -70,7 +72,10 @@ class Plan:
             e1.record()
             evs.append((e0, e1))
         torch.cuda.synchronize()
-        return [(m[0], e0.elapsed_time(e1), m[1]) for m, (e0, e1) in zip(self.meta, evs)]
+        rows = [(m[0], e0.elapsed_time(e1), m[1]) for m, (e0, e1) in zip(self.meta, evs)]
+        if Plan.detail_sink is not None:
+            Plan.detail_sink.extend((m[0], m[2], e0.elapsed_time(e1), m[1]) for m, (e0, e1) in zip(self.meta, evs))
+        return rows
 
     def __len__(self):
         return len(self.calls)
@@ -289,8 +294,11 @@ def make_conv_desc(n, h_in, w_in, cx, cin_off, cin, h_out, w_out, h_buf, w_buf, 
 def add_igemm(plan, desc, x, w, bias=None, res1=None, res2=None, mask=None, y=None):
     plan.keep(desc)
     flops = 2.0 * desc.n * desc.h_out * desc.w_out * desc.cout * desc.cin * desc.ntaps
+    info = "cin%d cout%d %dx%dx%d taps%d s%d%s%s" % (desc.cin, desc.cout, desc.n, desc.h_out, desc.w_out, desc.ntaps,
+                                                   desc.in_stride, " acc" if desc.accumulate else "",
+                                                   " up" if desc.upsample2x else "")
     plan.add(lib.b200_conv_igemm, C.byref(desc), P(x), P(w), P(bias), P(res1), P(res2), P(mask), P(y),
-             flops=flops, tag="conv_igemm")
+             flops=flops, tag="conv_igemm", info=info)
 
 
 def add_wgrad(plan, n, h_in, w_in, cx, x_coff, cin, h_out, w_out, cdy, dy_coff, cout, k, stride, pad,
@@ -299,4 +307,5 @@ def add_wgrad(plan, n, h_in, w_in, cx, x_coff, cin, h_out, w_out, cdy, dy_coff, 
                   scale)
     plan.keep(d)
     plan.add(lib.b200_conv_wgrad, C.byref(d), P(x), P(dy), P(dw), P(db),
-             flops=2.0 * n * h_out * w_out * cout * cin * k * k, tag="conv_wgrad")
+             flops=2.0 * n * h_out * w_out * cout * cin * k * k, tag="conv_wgrad",
+             info="cin%d cout%d %dx%dx%d k%d s%d" % (cin, cout, n, h_out, w_out, k, stride))
