@@ -64,6 +64,45 @@ int b200_conv_igemm(const b200_conv_desc* d, const void* x, const void* w_packed
                     const void* res1, const void* res2, const void* mask, void* y,
                     b200_stream_t stream);
 
+/* 3x3 stride-1 pad-1 convolution on ZERO-BORDERED ("flat") activations, the trunk fast path.
+ * Tensors are [n, h+2, w+2, c] NHWC bf16 whose 1-pixel border is zero and never written; with the
+ * border in place a tap is a pure row shift of the flattened [n*(h+2)*(w+2), c] matrix, so one
+ * haloed smem tile serves all 9 taps (9x less L2->SMEM traffic than per-tap loading):
+ *   out[m, cout_off+co] = epilogue( sum_t sum_ci in[m + tap_shift(t), cin_off+ci] * w[tap_w[t]][co][ci] )
+ * for interior positions m only.  tap_shift(t) = tap_dy[t]*(w+2) + tap_dx[t].  Epilogue as in
+ * b200_conv_igemm; res1/res2/mask are flat tensors indexed by the same m.
+ * out_mode 0: flat output [n,h+2,w+2,cy]; 1: dense [n,h,w,cy]; 2: dense with 2x2 replication
+ * [n,2h,2w,cy] (nearest upsample folded into the store).                                      */
+typedef struct {
+  int32_t n, h, w;              /* interior size; buffers are (h+2) x (w+2)                  */
+  int32_t cx, cin_off, cin;
+  int32_t cy, cout_off, cout;   /* cout % 16 == 0, cout <= 192                               */
+  int8_t tap_dy[9], tap_dx[9], tap_w[9];
+  int32_t out_mode;
+  int32_t w_taps, w_cout_pad, w_cin_pad;
+  float alpha;
+  int32_t act;
+  float slope;
+  float beta1, beta2;
+  int32_t res_nch, res1_c, res1_coff, res2_c, res2_coff;
+  int32_t accumulate;
+  int32_t mask_c, mask_coff, mask_lo, mask_hi;
+  float mask_slope;
+} b200_flat_desc;
+
+int b200_conv3x3_flat(const b200_flat_desc* d, const void* x, const void* w_packed, const float* bias,
+                      const void* res1, const void* res2, const void* mask, void* y,
+                      b200_stream_t stream);
+
+/* layout helpers between dense [n,h,w,c] and flat [n,h+2,w+2,c] slices (bf16):
+ * pad_copy:  flat[interior, dst_coff + c] = dense[.., src_coff + c]
+ * unpad_add: dense[.., c] = flat[interior, src_coff + c] (+ add[.., c] when add != NULL)       */
+int b200_pad_copy(void* dst_flat, int32_t dst_c, int32_t dst_coff, const void* src_dense, int32_t src_c,
+                  int32_t src_coff, int32_t n, int32_t h, int32_t w, int32_t c, b200_stream_t stream);
+int b200_unpad_add(void* dst_dense, int32_t dst_c, const void* src_flat, int32_t src_c, int32_t src_coff,
+                   const void* add_dense, int32_t add_c, int32_t n, int32_t h, int32_t w, int32_t c,
+                   b200_stream_t stream);
+
 /* Weight gradient of a conv (autograd wgrad of block.py:238):
  *   dw[co][ci][ky][kx] += scale * sum_{n,y,x} dy[n,y,x,dy_coff+co] * x[n, y*stride+ky-pad, x*stride+kx-pad, x_coff+ci]
  * dw is fp32 OIHW (the layout of nn.Conv2d.weight.grad); accumulated with fp32 atomics.      */

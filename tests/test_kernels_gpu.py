@@ -200,3 +200,52 @@ def test_pools_and_l1():
     fa, fb = rnd(2, 16, 16, 512, seed=5).to(BF), rnd(2, 16, 16, 512, seed=6).to(BF)
     loss, grad = ops.l1_loss_with_grad(fa, fb, 1.0)
     assert abs(float(loss) - float((fa.float() - fb.float()).abs().mean())) < 1e-4
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 24, 40, 64, 32), (1, 16, 16, 96, 32), (16, 64, 64, 160, 32),
+                                            (3, 64, 64, 192, 64), (2, 20, 12, 64, 192), (1, 8, 8, 32, 160)])
+def test_conv_flat_fwd(N, H, W, Cin, Cout):
+    """zero-bordered flat layout: one haloed smem tile feeds all 9 taps (shifted UMMA descriptors)"""
+    from trainner_b200 import ops
+    x = rnd(N, Cin, H, W, seed=1)
+    w = rnd(Cout, Cin, 3, 3, scale=(2.0 / (Cin * 9)) ** 0.5, seed=2)
+    b = rnd(Cout, scale=0.1, seed=3)
+    xf = ops.to_flat(nhwc(x))
+    y = ops.conv3x3_flat(xf, w, b, act=1, slope=0.2)
+    ref = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.2)
+    assert rel(nchw(ops.from_flat(y)), ref) < 4e-3
+    yb = nchw(y)  # border must stay exactly zero
+    assert float(yb[:, :, 0].abs().max()) == 0 and float(yb[:, :, -1].abs().max()) == 0
+    assert float(yb[:, :, :, 0].abs().max()) == 0 and float(yb[:, :, :, -1].abs().max()) == 0
+    y1 = ops.conv3x3_flat(xf, w, b, out_mode=1)
+    assert rel(nchw(y1), F.conv2d(x, w, b, padding=1)) < 4e-3
+    y2 = ops.conv3x3_flat(xf, w, b, out_mode=2)
+    assert rel(nchw(y2), F.interpolate(F.conv2d(x, w, b, padding=1), scale_factor=2.0, mode="nearest")) < 4e-3
+
+
+def test_conv_flat_rdb_semantics():
+    """slice in/out, residual epilogue, dgrad with accumulate + mask -- the RDB forward/backward ops"""
+    from trainner_b200 import ops
+    N, H, W = 2, 16, 24
+    buf = rnd(N, 192, H, W, seed=4)
+    w = rnd(64, 192, 3, 3, scale=0.03, seed=5)
+    b = rnd(64, scale=0.1, seed=6)
+    r2 = rnd(N, 192, H, W, seed=7)
+    bf_ = ops.to_flat(nhwc(buf))
+    out = ops.conv3x3_flat(bf_, w, b, alpha=0.04, res1=bf_, beta1=0.2, res2=ops.to_flat(nhwc(r2)), beta2=1.0,
+                           res_nch=64)
+    ref = 0.04 * F.conv2d(buf, w, b, padding=1) + 0.2 * buf[:, :64] + r2[:, :64]
+    assert rel(nchw(ops.from_flat(out)), ref) < 4e-3
+    # dgrad of a 96->32 conv whose dY lives in channels [96,128) of the gradient buffer
+    w2 = rnd(32, 96, 3, 3, scale=0.05, seed=8)
+    dbuf = rnd(N, 192, H, W, seed=9)
+    g = ops.to_flat(nhwc(dbuf))
+    ops.conv3x3_flat(g, w2, None, dgrad=True, cin_off=96, out=g, cout_off=0, accumulate=True, mask=bf_,
+                     mask_lo=64, mask_hi=96, mask_slope=0.2)
+    add = F.conv_transpose2d(dbuf[:, 96:128], w2, padding=1)
+    refg = dbuf.clone()
+    refg[:, :96] = dbuf[:, :96] + add
+    refg[:, 64:96] = torch.where(buf[:, 64:96] > 0, refg[:, 64:96], 0.2 * refg[:, 64:96])
+    got = nchw(ops.from_flat(g))
+    assert rel(got[:, :96], refg[:, :96]) < 5e-3
+    assert torch.equal(got[:, 96:], dbuf[:, 96:])

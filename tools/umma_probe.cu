@@ -62,6 +62,7 @@ struct Params {
   int a_mn;      // mode 3: A MN-major
 };
 
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ bool wait_bounded(uint64_t* bar, uint32_t parity) {
   for (long i = 0; i < 20000000L; ++i)
     if (mbar_try_wait(bar, parity)) return true;
@@ -73,13 +74,14 @@ probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
              Params p, float* __restrict__ D, long long* __restrict__ cycles, int* __restrict__ err) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint64_t bar_load, bar_mma, bar_mma2[4];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     mbar_init(&bar_load, 1);
     mbar_init(&bar_mma, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_mma2[i], 1);
     mbar_fence_init();
   }
   if (warp == 0) {
@@ -156,14 +158,15 @@ probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     }
   } else {
     // rate probe: zero operands resident in smem, 4 rotating stage addresses.
-    const uint32_t a_stage = 128 * 128;      // 16 KB (128 rows x 64 bf16)
+    const uint32_t a_stage = 144 * 128;      // 128 rows x 64 bf16 (+16 rows of slack for shifted starts)
     const uint32_t b_stage = 256 * 128;      // 32 KB
     for (uint32_t i = threadIdx.x; i < (4 * (a_stage + b_stage)) / 16; i += blockDim.x)
       reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     sB = sA + 4 * a_stage;
-    if (warp == 0) {
+    const int nissue = p.a_rows > 0 ? p.a_rows : 1;
+    if (warp < nissue) {
       // warp-uniform issue loop: operands live in uniform registers, one elected lane issues.
       const uint32_t idesc = make_idesc_bf16(128, p.N, p.a_mn, 0);
       const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
@@ -174,23 +177,23 @@ probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       long long t0 = clock64();
       for (int r = 0; r < p.reps; r += 4) {
         const int st = (r >> 2) & 3;
-        const uint32_t a_addr = a0 + st * a_stage, b_addr = b0 + st * b_stage;
+        const uint32_t a_addr = a0 + st * a_stage + p.shift * 128, b_addr = b0 + st * b_stage;
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             uint64_t ad = adesc_hi | (uint64_t)(((a_addr + k * a_kstep) >> 4) & 0x3FFF);
             uint64_t bd = bdesc_hi | (uint64_t)(((b_addr + k * 32) >> 4) & 0x3FFF);
-            umma_f16(tmem, ad, bd, idesc, (r | k) != 0);
+            umma_f16(tmem + warp * 128 + ((p.base_off && (k & 1)) ? 64 : 0), ad, bd, idesc, (r | k) > 1);
           }
         }
         __syncwarp();
       }
-      if (elect_one()) umma_commit(&bar_mma);
+      if (elect_one()) umma_commit(&bar_mma2[warp]);
       __syncwarp();
-      ok = wait_bounded(&bar_mma, 0);
+      ok = wait_bounded(&bar_mma2[warp], 0);
       long long t1 = clock64();
-      if (threadIdx.x == 0) {
-        cycles[blockIdx.x] = t1 - t0;
+      if (lane_id() == 0) {
+        atomicMax((unsigned long long*)&cycles[blockIdx.x], (unsigned long long)(t1 - t0));
         if (!ok) *err = 1;
       }
     }
@@ -261,6 +264,7 @@ int main(int argc, char** argv) {
   cases.push_back({"mnmajor_B_sw64", {2, 32, 128, 0, 0, 128, 0, 0}});
   cases.push_back({"mnmajor_B_sw64_shift", {2, 32, 128, 5, 0, 136, 0, 0}});
 
+  if (argc > 1 && !strcmp(argv[1], "rate")) cases.clear();
   for (auto& cs : cases) {
     Params p = cs.p;
     // host data
@@ -353,23 +357,23 @@ int main(int argc, char** argv) {
   {
     CUtensorMap dummy;
     memset(&dummy, 0, sizeof(dummy));
-    for (int grid : {1, 148})
-      for (int a_mn : {0, 1})
-        for (int N : {16, 32, 64, 96, 128, 192, 256}) {
-          Params p = {3, N, 0, 0, 0, 0, 4096, a_mn};
+    for (int nissue : {1, 2, 4})
+      for (int N : {16, 32, 64, 128}) {
+          Params p = {3, N, 0, 0, 0, nissue, 4096, 0};
           CK(cudaMemset(derr, 0, sizeof(int)));
-          probe_kernel<<<grid, 128, SMEM>>>(dummy, dummy, p, dD, dcyc, derr);
+          CK(cudaMemset(dcyc, 0, 1024 * sizeof(long long)));
+          probe_kernel<<<148, 128, SMEM>>>(dummy, dummy, p, dD, dcyc, derr);
           CK(cudaDeviceSynchronize());
-          probe_kernel<<<grid, 128, SMEM>>>(dummy, dummy, p, dD, dcyc, derr);
+          CK(cudaMemset(dcyc, 0, 1024 * sizeof(long long)));
+          probe_kernel<<<148, 128, SMEM>>>(dummy, dummy, p, dD, dcyc, derr);
           CK(cudaDeviceSynchronize());
-          std::vector<long long> cyc(grid);
-          CK(cudaMemcpy(cyc.data(), dcyc, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+          std::vector<long long> cyc(148);
+          CK(cudaMemcpy(cyc.data(), dcyc, 148 * sizeof(long long), cudaMemcpyDeviceToHost));
           long long mx = 0;
           for (auto c : cyc) mx = c > mx ? c : mx;
-          double per = (double)mx / p.reps;
-          printf("rate grid=%3d a_mn=%d N=%3d : %.1f cyc/MMA (ideal %.1f) -> %.0f%% of tensor peak\n",
-                 grid, a_mn, N, per, N / 2.0, 100.0 * (N / 2.0) / per);
-        }
+          double per = (double)mx / (p.reps * nissue);
+          printf("rate issuers=%d N=%3d : %.1f cyc/MMA aggregate (ideal %.1f)\n", nissue, N, per, N / 2.0);
+      }
   }
   printf("done\n");
   return 0;

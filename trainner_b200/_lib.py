@@ -35,6 +35,24 @@ class ConvDesc(C.Structure):
     ]
 
 
+class FlatDesc(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("cx", C.c_int32), ("cin_off", C.c_int32), ("cin", C.c_int32),
+        ("cy", C.c_int32), ("cout_off", C.c_int32), ("cout", C.c_int32),
+        ("tap_dy", C.c_int8 * 9), ("tap_dx", C.c_int8 * 9), ("tap_w", C.c_int8 * 9),
+        ("out_mode", C.c_int32),
+        ("w_taps", C.c_int32), ("w_cout_pad", C.c_int32), ("w_cin_pad", C.c_int32),
+        ("alpha", C.c_float), ("act", C.c_int32), ("slope", C.c_float),
+        ("beta1", C.c_float), ("beta2", C.c_float),
+        ("res_nch", C.c_int32), ("res1_c", C.c_int32), ("res1_coff", C.c_int32),
+        ("res2_c", C.c_int32), ("res2_coff", C.c_int32),
+        ("accumulate", C.c_int32),
+        ("mask_c", C.c_int32), ("mask_coff", C.c_int32), ("mask_lo", C.c_int32), ("mask_hi", C.c_int32),
+        ("mask_slope", C.c_float),
+    ]
+
+
 class WgradDesc(C.Structure):
     _fields_ = [
         ("n", C.c_int32), ("h_in", C.c_int32), ("w_in", C.c_int32), ("cx", C.c_int32),
@@ -59,6 +77,9 @@ _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 _SIGNATURES = {
     "b200_conv_igemm": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P],
+    "b200_conv3x3_flat": [C.POINTER(FlatDesc), _P, _P, _P, _P, _P, _P, _P, _P],
+    "b200_pad_copy": [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    "b200_unpad_add": [_P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P],
     "b200_conv_wgrad": [C.POINTER(WgradDesc), _P, _P, _P, _P, _P],
     "b200_pack_weights": [_P, _I, _I, _P],
     "b200_conv3x3_thin_to_wide": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _F,

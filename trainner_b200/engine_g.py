@@ -1,6 +1,8 @@
 """Fused forward/backward engine of the RRDBNet generator (reference: RRDBNet_arch.py:14-163).
 
-HBM layout: every RDB owns ONE NHWC bf16 buffer [N, h, w, nf + 4*gc]; conv_k reads channels
+HBM layout: every RDB owns ONE zero-bordered ("flat") NHWC bf16 buffer [N, h+2, w+2, nf + 4*gc]
+(conv_flat.cu: with the border stored, a conv tap is a row shift of the flattened matrix and one
+haloed smem tile feeds all 9 taps); conv_k reads channels
 [0, nf+(k-1)gc) and writes its LeakyReLU'd output into channels [nf+(k-1)gc, nf+k*gc) -- the
 reference's four torch.cat copies per RDB do not exist.  conv5's epilogue writes
 0.2*conv5 + x (and, for the third RDB of an RRDB, the RRDB residual too) straight into channels
@@ -16,7 +18,8 @@ import torch
 from . import _lib
 from ._lib import lib
 from .runtime import (ConvLayer, ContextPool, FlatGrads, Lease, LRELU_SLOPE, P, Plan, WeightPacker,
-                      add_igemm, add_wgrad, make_conv_desc, require_device, taps_conv, taps_dgrad_s1)
+                      add_flat, add_igemm, add_wgrad, make_conv_desc, make_flat_desc, require_device, taps_conv,
+                      taps_dgrad_s1)
 
 BF16 = torch.bfloat16
 
@@ -64,8 +67,10 @@ class RRDBNetEngine:
         ctx.shape = (N, h, w)
         e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)
         ctx.x = torch.empty(N, net.in_nc, h, w, dtype=torch.float32, device=dev)
-        ctx.B = [e(N, h, w, C) for _ in range(nrdb)] + [e(N, h, w, nf)]
+        z = lambda *s: torch.zeros(*s, dtype=BF16, device=dev)
+        ctx.B = [z(N, h + 2, w + 2, C) for _ in range(nrdb)] + [z(N, h + 2, w + 2, nf)]   # flat, zero border
         Bc = [C] * nrdb + [nf]
+        ctx.F0 = e(N, h, w, nf)
         # upsampler chain: U[i] is the (already nearest-upsampled) input of upconv i
         ctx.U = []
         hh, ww = h, w
@@ -80,32 +85,31 @@ class RRDBNetEngine:
 
         # ---------------- forward plan
         f = Plan()
-        f.add(lib.b200_conv3x3_thin_to_wide, P(ctx.x), P(self.fea.weight), P(self.fea.bias), P(ctx.B[0]),
-              N, h, w, net.in_nc, nf, Bc[0], 0, 0, None, None, 0, 0.0, None, 0, 0, 0.0)
+        f.add(lib.b200_conv3x3_thin_to_wide, P(ctx.x), P(self.fea.weight), P(self.fea.bias), P(ctx.F0),
+              N, h, w, net.in_nc, nf, nf, 0, 0, None, None, 0, 0.0, None, 0, 0, 0.0)
+        f.add(lib.b200_pad_copy, P(ctx.B[0]), Bc[0], 0, P(ctx.F0), nf, 0, N, h, w, nf)
         for r, convs in enumerate(self.rdbs):
             Bi, Bo = ctx.B[r], ctx.B[r + 1]
             for kk in range(4):
                 L = convs[kk]
                 cin = nf + kk * gc
-                d = make_conv_desc(N, h, w, C, 0, cin, h, w, h, w, C, cin, gc, taps_conv(3, 1), L.taps,
-                                   L.fwd_rows, L.fwd_cols, act=1, slope=LRELU_SLOPE)
-                add_igemm(f, d, Bi, L.w_fwd, L.bias, y=Bi)
+                d = make_flat_desc(N, h, w, C, 0, cin, C, cin, gc, taps_conv(3, 1), L.taps, L.fwd_rows, L.fwd_cols,
+                                   act=1, slope=LRELU_SLOPE)
+                add_flat(f, d, Bi, L.w_fwd, L.bias, y=Bi)
             L = convs[4]
             last_of_rrdb = (r % 3 == 2)
             a = 0.04 if last_of_rrdb else 0.2
             b1 = 0.2 if last_of_rrdb else 1.0
-            d = make_conv_desc(N, h, w, C, 0, C, h, w, h, w, Bc[r + 1], 0, nf, taps_conv(3, 1), L.taps,
-                               L.fwd_rows, L.fwd_cols, alpha=a, beta1=b1, res_nch=nf, res1_c=C,
-                               res1_coff=0, beta2=1.0 if last_of_rrdb else 0.0, res2_c=C, res2_coff=0)
-            add_igemm(f, d, Bi, L.w_fwd, L.bias, res1=Bi, res2=ctx.B[r - 2] if last_of_rrdb else None, y=Bo)
-        # LR_conv + shortcut (+ nearest x2 folded into the store when an upconv follows)
+            d = make_flat_desc(N, h, w, C, 0, C, Bc[r + 1], 0, nf, taps_conv(3, 1), L.taps, L.fwd_rows, L.fwd_cols,
+                               alpha=a, beta1=b1, res_nch=nf, res1_c=C, res1_coff=0,
+                               beta2=1.0 if last_of_rrdb else 0.0, res2_c=C, res2_coff=0)
+            add_flat(f, d, Bi, L.w_fwd, L.bias, res1=Bi, res2=ctx.B[r - 2] if last_of_rrdb else None, y=Bo)
+        # LR_conv + shortcut (+ nearest x2 folded into the store when an upconv follows); dense output
         L = self.lr
         first_dst = ctx.U[0] if self.ups else ctx.V
-        hb, wb = (2 * h, 2 * w) if self.ups else (h, w)
-        d = make_conv_desc(N, h, w, nf, 0, nf, h, w, hb, wb, nf, 0, nf, taps_conv(3, 1), L.taps, L.fwd_rows,
-                           L.fwd_cols, upsample=1 if self.ups else 0, beta1=1.0, res_nch=nf, res1_c=Bc[0],
-                           res1_coff=0)
-        add_igemm(f, d, ctx.B[nrdb], L.w_fwd, L.bias, res1=ctx.B[0], y=first_dst)
+        d = make_flat_desc(N, h, w, nf, 0, nf, nf, 0, nf, taps_conv(3, 1), L.taps, L.fwd_rows, L.fwd_cols,
+                           out_mode=2 if self.ups else 1, beta1=1.0, res_nch=nf, res1_c=Bc[0], res1_coff=0)
+        add_flat(f, d, ctx.B[nrdb], L.w_fwd, L.bias, res1=ctx.B[0], y=first_dst)
         hh, ww = h, w
         for i, L in enumerate(self.ups):
             hh, ww = hh * 2, ww * 2
@@ -140,7 +144,9 @@ class RRDBNetEngine:
         ctx.dV = e(N, H, W, nf)
         ctx.dU = [e(*u.shape) for u in ctx.U]
         ctx.dP = [e(u.shape[0], u.shape[1] // 2, u.shape[2] // 2, nf) for u in ctx.U]
-        ctx.G = [e(N, h, w, C) for _ in range(4)]
+        ctx.G = [torch.zeros(N, h + 2, w + 2, C, dtype=BF16, device=dev) for _ in range(4)]  # flat
+        ctx.dFea = e(N, h, w, nf)
+        Hp, Wp = h + 2, w + 2
         b = Plan()
         SL = LRELU_SLOPE
         # HR_conv1 (wide->thin) backward
@@ -172,10 +178,12 @@ class RRDBNetEngine:
         dT = dcur  # gradient wrt (fea + LR_conv(trunk)) at LR resolution
         slot = lambda r: ctx.G[r % 4]
         L = self.lr
-        d = make_conv_desc(N, h, w, nf, 0, nf, h, w, h, w, C, 0, nf, taps_dgrad_s1(3, 1), L.taps, L.dgr_rows,
-                           L.dgr_cols)
+        # dT is dense [N,h,w,nf]; its dgrad lands in the interior of the flat gradient buffer
+        d = make_conv_desc(N, h, w, nf, 0, nf, h, w, Hp, Wp, C, 0, nf, taps_dgrad_s1(3, 1), L.taps, L.dgr_rows,
+                           L.dgr_cols, out_off=(1, 1))
         add_igemm(b, d, dT, L.w_dgr, y=slot(nrdb))
-        add_wgrad(b, N, h, w, nf, 0, nf, h, w, nf, 0, nf, 3, 1, 1, 1.0, ctx.B[nrdb], dT, g(L.weight), g(L.bias))
+        # x flat (its own border is the conv's zero padding -> pad 0 on the flat grid), dy dense
+        add_wgrad(b, N, Hp, Wp, nf, 0, nf, h, w, nf, 0, nf, 3, 1, 0, 1.0, ctx.B[nrdb], dT, g(L.weight), g(L.bias))
         for r in range(nrdb - 1, -1, -1):
             convs = self.rdbs[r]
             Gr, dO, Br = slot(r), slot(r + 1), ctx.B[r]
@@ -184,26 +192,26 @@ class RRDBNetEngine:
             a = 0.04 if last_of_rrdb else 0.2
             b1 = 0.2 if last_of_rrdb else 1.0
             L = convs[4]
-            d = make_conv_desc(N, h, w, C, 0, nf, h, w, h, w, C, 0, C, taps_dgrad_s1(3, 1), L.taps, L.dgr_rows,
-                               L.dgr_cols, alpha=a, beta1=b1, res_nch=nf, res1_c=C, res1_coff=0,
-                               beta2=1.0 if first_of_rrdb else 0.0, res2_c=C, res2_coff=0, mask_c=C,
-                               mask_coff=0, mask_lo=nf + 3 * gc, mask_hi=C, mask_slope=SL)
-            add_igemm(b, d, dO, L.w_dgr, res1=dO, res2=slot(r + 3) if first_of_rrdb else None, mask=Br, y=Gr)
-            add_wgrad(b, N, h, w, C, 0, C, h, w, C, 0, nf, 3, 1, 1, a, Br, dO, g(L.weight), g(L.bias))
+            d = make_flat_desc(N, h, w, C, 0, nf, C, 0, C, taps_dgrad_s1(3, 1), L.taps, L.dgr_rows, L.dgr_cols,
+                               alpha=a, beta1=b1, res_nch=nf, res1_c=C, res1_coff=0,
+                               beta2=1.0 if first_of_rrdb else 0.0, res2_c=C, res2_coff=0, mask_c=C, mask_coff=0,
+                               mask_lo=nf + 3 * gc, mask_hi=C, mask_slope=SL)
+            add_flat(b, d, dO, L.w_dgr, res1=dO, res2=slot(r + 3) if first_of_rrdb else None, mask=Br, y=Gr)
+            # wgrads run on the whole flat grid: the zero borders of x and dy contribute nothing
+            add_wgrad(b, N, Hp, Wp, C, 0, C, Hp, Wp, C, 0, nf, 3, 1, 1, a, Br, dO, g(L.weight), g(L.bias))
             for kk in range(3, -1, -1):
                 L = convs[kk]
                 lo = nf + kk * gc  # this conv's output slice [lo, lo+gc) == its dY; inputs are [0, lo)
-                d = make_conv_desc(N, h, w, C, lo, gc, h, w, h, w, C, 0, lo, taps_dgrad_s1(3, 1), L.taps,
-                                   L.dgr_rows, L.dgr_cols, accumulate=1, mask_c=C, mask_coff=0,
-                                   mask_lo=lo - gc if kk > 0 else 0, mask_hi=lo if kk > 0 else 0,
-                                   mask_slope=SL)
-                add_igemm(b, d, Gr, L.w_dgr, mask=Br if kk > 0 else None, y=Gr)
-                add_wgrad(b, N, h, w, C, 0, lo, h, w, C, lo, gc, 3, 1, 1, 1.0, Br, Gr, g(L.weight), g(L.bias))
-        # shortcut: d(fea) = G[0][0:nf] + dT
+                d = make_flat_desc(N, h, w, C, lo, gc, C, 0, lo, taps_dgrad_s1(3, 1), L.taps, L.dgr_rows, L.dgr_cols,
+                                   accumulate=1, mask_c=C, mask_coff=0, mask_lo=lo - gc if kk > 0 else 0,
+                                   mask_hi=lo if kk > 0 else 0, mask_slope=SL)
+                add_flat(b, d, Gr, L.w_dgr, mask=Br if kk > 0 else None, y=Gr)
+                add_wgrad(b, N, Hp, Wp, C, 0, lo, Hp, Wp, C, lo, gc, 3, 1, 1, 1.0, Br, Gr, g(L.weight), g(L.bias))
+        # shortcut: d(fea) = interior(G[0][0:nf]) + dT  (dense), then the thin conv's weight gradient
         G0 = slot(0)
-        b.add(lib.b200_add_slice_bf16, P(G0), C, 0, P(dT), nf, 0, N * h * w, nf)
-        b.add(lib.b200_conv3x3_thin_wgrad, P(ctx.x), P(G0), P(g(self.fea.weight)), P(g(self.fea.bias)), None,
-              N, h, w, net.in_nc, nf, C, 0, 1, None, None)
+        b.add(lib.b200_unpad_add, P(ctx.dFea), nf, P(G0), C, 0, P(dT), nf, N, h, w, nf)
+        b.add(lib.b200_conv3x3_thin_wgrad, P(ctx.x), P(ctx.dFea), P(g(self.fea.weight)), P(g(self.fea.bias)), None,
+              N, h, w, net.in_nc, nf, nf, 0, 1, None, None)
         ctx.bwd = b
 
     # ------------------------------------------------------------------ run

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 from ._lib import PackEntry, WgradDesc, lib
-from .runtime import (make_conv_desc, require_device, roundup, stream_ptr, taps_conv, taps_dgrad_s1,
+from .runtime import (make_conv_desc, make_flat_desc, require_device, roundup, stream_ptr, taps_conv, taps_dgrad_s1,
                       taps_dgrad_s2_k4)
 
 BF16 = torch.bfloat16
@@ -215,3 +215,50 @@ def l1_loss_with_grad(a, b, weight=1.0):
     fn = lib.b200_l1_loss_f32 if a.dtype == torch.float32 else lib.b200_l1_loss_bf16
     _lib.check(fn(_p(a), _p(b), _p(loss), _p(grad), a.numel(), float(weight), stream_ptr()), "l1_loss")
     return loss[0], grad
+
+
+def to_flat(x_dense, c_total=None, coff=0):
+    """dense [N,H,W,C] -> zero-bordered flat [N,H+2,W+2,c_total] with x at channels [coff, coff+C)."""
+    require_device(x_dense, "to_flat")
+    N, H, W, Cc = x_dense.shape
+    ct = Cc if c_total is None else c_total
+    out = torch.zeros(N, H + 2, W + 2, ct, dtype=BF16, device=x_dense.device)
+    _lib.check(lib.b200_pad_copy(_p(out), ct, coff, _p(x_dense), Cc, 0, N, H, W, Cc, stream_ptr()), "pad_copy")
+    return out
+
+
+def from_flat(x_flat, coff=0, c=None, add=None):
+    require_device(x_flat, "from_flat")
+    N, Hp, Wp, Ct = x_flat.shape
+    c = Ct - coff if c is None else c
+    out = torch.empty(N, Hp - 2, Wp - 2, c, dtype=BF16, device=x_flat.device)
+    _lib.check(lib.b200_unpad_add(_p(out), c, _p(x_flat), Ct, coff, _p(add), add.shape[3] if add is not None else 8,
+                                  N, Hp - 2, Wp - 2, c, stream_ptr()), "unpad_add")
+    return out
+
+
+def conv3x3_flat(x_flat, w_oihw, bias=None, dgrad=False, cin_off=0, out=None, cout_off=0, out_mode=0, act=0,
+                 slope=0.2, alpha=1.0, res1=None, res1_coff=0, beta1=0.0, res2=None, res2_coff=0, beta2=0.0,
+                 res_nch=0, accumulate=False, mask=None, mask_coff=0, mask_lo=0, mask_hi=0, mask_slope=0.2):
+    """3x3 s1 p1 conv (or its input gradient when dgrad=True) on zero-bordered flat tensors."""
+    require_device(x_flat, "conv3x3_flat")
+    N, Hp, Wp, Cx = x_flat.shape
+    h, w = Hp - 2, Wp - 2
+    Cout, Cin, kh, kw = w_oihw.shape
+    assert kh == 3 and kw == 3
+    K, Nout = (Cout, Cin) if dgrad else (Cin, Cout)
+    wp = pack_weight(w_oihw, 1 if dgrad else 0)
+    taps = taps_dgrad_s1(3, 1) if dgrad else taps_conv(3, 1)
+    if out is None:
+        shape = {0: (N, Hp, Wp, Nout), 1: (N, h, w, Nout), 2: (N, 2 * h, 2 * w, Nout)}[out_mode]
+        out = torch.zeros(*shape, dtype=BF16, device=x_flat.device)
+    d = make_flat_desc(N, h, w, Cx, cin_off, K, out.shape[3], cout_off, Nout, taps, 9, wp.shape[1], wp.shape[2],
+                       out_mode=out_mode, alpha=alpha, act=act, slope=slope, beta1=beta1, beta2=beta2,
+                       res_nch=res_nch, res1_c=res1.shape[3] if res1 is not None else 0, res1_coff=res1_coff,
+                       res2_c=res2.shape[3] if res2 is not None else 0, res2_coff=res2_coff,
+                       accumulate=1 if accumulate else 0, mask_c=mask.shape[3] if mask is not None else 0,
+                       mask_coff=mask_coff, mask_lo=mask_lo, mask_hi=mask_hi, mask_slope=mask_slope)
+    b = bias.detach().float().contiguous() if bias is not None else None
+    _lib.check(lib.b200_conv3x3_flat(C.byref(d), _p(x_flat), _p(wp), _p(b), _p(res1), _p(res2), _p(mask), _p(out),
+                                     stream_ptr()), "conv3x3_flat")
+    return out

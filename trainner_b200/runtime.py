@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, PackEntry, WgradDesc, lib
+from ._lib import ConvDesc, FlatDesc, PackEntry, WgradDesc, lib
 
 LRELU_SLOPE = 0.2
 
@@ -309,3 +309,29 @@ def add_wgrad(plan, n, h_in, w_in, cx, x_coff, cin, h_out, w_out, cdy, dy_coff, 
     plan.add(lib.b200_conv_wgrad, C.byref(d), P(x), P(dy), P(dw), P(db),
              flops=2.0 * n * h_out * w_out * cout * cin * k * k, tag="conv_wgrad",
              info="cin%d cout%d %dx%dx%d k%d s%d" % (cin, cout, n, h_out, w_out, k, stride))
+
+
+def make_flat_desc(n, h, w, cx, cin_off, cin, cy, cout_off, cout, taps, w_taps, w_rows, w_cols, out_mode=0,
+                   alpha=1.0, act=0, slope=0.0, beta1=0.0, beta2=0.0, res_nch=0, res1_c=0, res1_coff=0,
+                   res2_c=0, res2_coff=0, accumulate=0, mask_c=0, mask_coff=0, mask_lo=0, mask_hi=0,
+                   mask_slope=0.0):
+    d = FlatDesc()
+    d.n, d.h, d.w, d.cx, d.cin_off, d.cin, d.cy, d.cout_off, d.cout = n, h, w, cx, cin_off, cin, cy, cout_off, cout
+    assert len(taps) == 9
+    for i, (dy, dx, wi) in enumerate(taps):
+        d.tap_dy[i], d.tap_dx[i], d.tap_w[i] = dy, dx, wi
+    d.out_mode = out_mode
+    d.w_taps, d.w_cout_pad, d.w_cin_pad = w_taps, w_rows, w_cols
+    d.alpha, d.act, d.slope, d.beta1, d.beta2 = alpha, act, slope, beta1, beta2
+    d.res_nch, d.res1_c, d.res1_coff, d.res2_c, d.res2_coff = res_nch, res1_c, res1_coff, res2_c, res2_coff
+    d.accumulate = accumulate
+    d.mask_c, d.mask_coff, d.mask_lo, d.mask_hi, d.mask_slope = mask_c, mask_coff, mask_lo, mask_hi, mask_slope
+    return d
+
+
+def add_flat(plan, desc, x, w, bias=None, res1=None, res2=None, mask=None, y=None):
+    plan.keep(desc)
+    flops = 2.0 * desc.n * desc.h * desc.w * desc.cout * desc.cin * 9
+    info = "cin%d cout%d %dx%dx%d%s" % (desc.cin, desc.cout, desc.n, desc.h, desc.w, " acc" if desc.accumulate else "")
+    plan.add(lib.b200_conv3x3_flat, C.byref(desc), P(x), P(w), P(bias), P(res1), P(res2), P(mask), P(y),
+             flops=flops, tag="conv_flat", info=info)
