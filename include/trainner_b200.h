@@ -76,6 +76,8 @@ int b200_conv_igemm(const b200_conv_desc* d, const void* x, const void* w_packed
 typedef struct {
   int32_t n, h, w;              /* interior size; buffers are (h+2) x (w+2)                  */
   int32_t cx, cin_off, cin;
+  int32_t cx2, cin2_off, cin2;  /* optional second input (flat, same grid): its channels extend the
+                                   reduction axis after the first input's (cin padded to 64)     */
   int32_t cy, cout_off, cout;   /* cout % 16 == 0, cout <= 192                               */
   int8_t tap_dy[9], tap_dx[9], tap_w[9];
   int32_t out_mode;
@@ -90,8 +92,8 @@ typedef struct {
   float mask_slope;
 } b200_flat_desc;
 
-int b200_conv3x3_flat(const b200_flat_desc* d, const void* x, const void* w_packed, const float* bias,
-                      const void* res1, const void* res2, const void* mask, void* y,
+int b200_conv3x3_flat(const b200_flat_desc* d, const void* x, const void* x2, const void* w_packed,
+                      const float* bias, const void* res1, const void* res2, const void* mask, void* y,
                       b200_stream_t stream);
 
 /* layout helpers between dense [n,h,w,c] and flat [n,h+2,w+2,c] slices (bf16):
@@ -116,6 +118,35 @@ typedef struct {
 int b200_conv_wgrad(const b200_wgrad_desc* d, const void* x, const void* dy, float* dw,
                     float* dbias, b200_stream_t stream);
 
+/* Weight gradients of ALL residual dense blocks in one launch (flat layout, nf = 64, gc = 32).
+ * Per block r: x = B[r] [P,192], g = G[r] (conv1..4 pre-activation grads in channels 64..191),
+ * dO = G[r+1][:, 0:64] (conv5's dY up to scale5).  dw[k] are the fp32 OIHW gradient tensors of
+ * conv1..conv5 (accumulated with +=).  Tensor maps are encoded on the host into `maps_host`
+ * (3 * n_rdb * b200_tensor_map_bytes() bytes, 64-byte aligned) and copied to the device by the caller. */
+typedef struct {
+  float* dw[5];
+  float scale5;
+  int32_t pad_;
+} b200_wgrad_rdb_entry;
+
+int b200_tensor_map_bytes(void);
+int b200_wgrad_rdb_make_maps(void* maps_host, int32_t n_rdb, const void* const* x_ptrs,
+                             const void* const* g_ptrs, const void* const* do_ptrs,
+                             const int32_t* do_pitch, int32_t n, int32_t h, int32_t w, int32_t c);
+int b200_wgrad_rdb(const void* maps_dev, const b200_wgrad_rdb_entry* entries_dev, int32_t n_rdb,
+                   int32_t n, int32_t h, int32_t w, int32_t nf, int32_t gc, b200_stream_t stream);
+
+/* Many per-channel column sums in one launch: dst[c] += scale * sum_p src[p*pitch + coff + c]  (bias grads) */
+typedef struct {
+  const void* src;   /* bf16 */
+  float* dst;
+  int64_t npix;
+  int32_t pitch, coff, c;
+  float scale;
+} b200_colsum_entry;
+
+int b200_colsum_multi(const b200_colsum_entry* table_dev, int32_t count, b200_stream_t stream);
+
 /* Pack fp32 OIHW conv weights into the bf16 tensor-core layouts, many tensors per launch.
  * table: device array of b200_pack_entry.  mode 0: [tap][co][ci] (fwd); 1: [tap][ci][co] (dgrad) */
 typedef struct {
@@ -127,6 +158,21 @@ typedef struct {
 
 int b200_pack_weights(const b200_pack_entry* table_dev, int32_t count, int32_t max_elems,
                       b200_stream_t stream);
+
+/* Pack a block of an fp32 OIHW weight into a column range of a concatenated dgrad matrix
+ * dst[tap][row][col_off + co] = scale * src[co][ci_off + row][tap] for row < n_rows, co < cout
+ * (dst is bf16 [taps][rows_pad][cols_pad], zero-initialised once by the caller).  Used by the
+ * gather form of the RDB input gradient: one GEMM per channel slice over all later convs.     */
+typedef struct {
+  const float* src;
+  void* dst;
+  int32_t cout, cin, taps, ci_off, n_rows, rows_pad, cols_pad, col_off;
+  float scale;
+  int32_t pad_;
+} b200_packcat_entry;
+
+int b200_pack_cat(const b200_packcat_entry* table_dev, int32_t count, int32_t max_elems,
+                  b200_stream_t stream);
 
 /* 3x3 stride-1 pad-1 convolutions with a thin (<= 4 channel) side, CUDA-core direct kernels.
  * thin->wide: x NCHW fp32 [n,cs,h,w] -> y NHWC bf16 [n,h,w,cy] slice, optional per-channel input

@@ -20,10 +20,10 @@ for name, (cin, cout, dgrad) in cases.items():
     if dgrad:
         d = make_flat_desc(N, H, W, C_, 64, cin, C_, 0, cout, taps_dgrad_s1(3, 1), 9, wp.shape[1], wp.shape[2],
                            accumulate=1, mask_c=C_, mask_lo=cout - 32, mask_hi=cout, mask_slope=0.2)
-        args = (C.byref(d), g.data_ptr(), wp.data_ptr(), None, None, None, x.data_ptr(), g.data_ptr())
+        args = (C.byref(d), g.data_ptr(), None, wp.data_ptr(), None, None, None, x.data_ptr(), g.data_ptr())
     else:
         d = make_flat_desc(N, H, W, C_, 0, cin, C_, 160, cout, taps_conv(3, 1), 9, wp.shape[1], wp.shape[2], act=1, slope=0.2)
-        args = (C.byref(d), x.data_ptr(), wp.data_ptr(), None, None, None, None, x.data_ptr())
+        args = (C.byref(d), x.data_ptr(), None, wp.data_ptr(), None, None, None, None, x.data_ptr())
     s = stream_ptr()
     for _ in range(3):
         assert lib.b200_conv3x3_flat(*args, s) == 0

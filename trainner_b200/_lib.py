@@ -39,6 +39,7 @@ class FlatDesc(C.Structure):
     _fields_ = [
         ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
         ("cx", C.c_int32), ("cin_off", C.c_int32), ("cin", C.c_int32),
+        ("cx2", C.c_int32), ("cin2_off", C.c_int32), ("cin2", C.c_int32),
         ("cy", C.c_int32), ("cout_off", C.c_int32), ("cout", C.c_int32),
         ("tap_dy", C.c_int8 * 9), ("tap_dx", C.c_int8 * 9), ("tap_w", C.c_int8 * 9),
         ("out_mode", C.c_int32),
@@ -64,6 +65,22 @@ class WgradDesc(C.Structure):
     ]
 
 
+class WgradRdbEntry(C.Structure):
+    _fields_ = [("dw", C.c_void_p * 5), ("scale5", C.c_float), ("pad_", C.c_int32)]
+
+
+class ColsumEntry(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("npix", C.c_int64),
+                ("pitch", C.c_int32), ("coff", C.c_int32), ("c", C.c_int32), ("scale", C.c_float)]
+
+
+class PackCatEntry(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p),
+                ("cout", C.c_int32), ("cin", C.c_int32), ("taps", C.c_int32), ("ci_off", C.c_int32),
+                ("n_rows", C.c_int32), ("rows_pad", C.c_int32), ("cols_pad", C.c_int32), ("col_off", C.c_int32),
+                ("scale", C.c_float), ("pad_", C.c_int32)]
+
+
 class PackEntry(C.Structure):
     _fields_ = [
         ("src", C.c_void_p), ("dst", C.c_void_p),
@@ -77,10 +94,14 @@ _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 _SIGNATURES = {
     "b200_conv_igemm": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P],
-    "b200_conv3x3_flat": [C.POINTER(FlatDesc), _P, _P, _P, _P, _P, _P, _P, _P],
+    "b200_conv3x3_flat": [C.POINTER(FlatDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "b200_pack_cat": [_P, _I, _I, _P],
     "b200_pad_copy": [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_unpad_add": [_P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P],
     "b200_conv_wgrad": [C.POINTER(WgradDesc), _P, _P, _P, _P, _P],
+    "b200_wgrad_rdb_make_maps": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I],
+    "b200_wgrad_rdb": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "b200_colsum_multi": [_P, _I, _P],
     "b200_pack_weights": [_P, _I, _I, _P],
     "b200_conv3x3_thin_to_wide": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _F,
                                   _P, _I, _I, _F, _P],
@@ -104,7 +125,7 @@ _SIGNATURES = {
 }
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["b200_last_error", "b200_version", "b200_device_ok",
-                                                "b200_launch_count"])
+                                                "b200_launch_count", "b200_tensor_map_bytes"])
 
 
 def _load():
@@ -121,6 +142,8 @@ def _load():
     lib.b200_version.restype = C.c_int
     lib.b200_device_ok.restype = C.c_int
     lib.b200_launch_count.restype = C.c_int64
+    lib.b200_tensor_map_bytes.restype = C.c_int
+    lib.b200_tensor_map_bytes.argtypes = []
     return lib
 
 

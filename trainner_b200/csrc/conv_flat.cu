@@ -29,10 +29,12 @@ constexpr int kTileM = 256;
 
 struct FlatParams {
   CUtensorMap in_map;  // 2-D [P rows][C extent], box (64, box_rows)
+  CUtensorMap in2_map; // optional second input (extends the reduction axis)
   CUtensorMap w_map;   // 3-D packed weights, box (64, BN, 1)
   int P, Hp, Wp, HpWp, h, w, n;
   int total_tiles;
-  int cin_off, k_chunks, last_k16;
+  int cin_off, k_chunks, last_k16;      // k_chunks = kc1 + kc2
+  int kc1, last1_k16, cin2_off;
   int tap_shift[9];
   int tap_w[9];
   int halo;            // Wp + 1
@@ -195,7 +197,8 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
     mbar_fence_init();
   }
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.in_map);
+    if (p.kc1) tma_prefetch_desc(&p.in_map);
+    if (p.k_chunks > p.kc1) tma_prefetch_desc(&p.in2_map);
     tma_prefetch_desc(&p.w_map);
   }
   if (warp == 1) {
@@ -219,9 +222,10 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
         if (elect_one()) {
           uint8_t* sa = smem + (size_t)as * p.a_stage_bytes;
           mbar_expect_tx(&a_full[as], p.a_bytes);
+          const CUtensorMap* im = (c < p.kc1) ? &p.in_map : &p.in2_map;
+          const int ch = (c < p.kc1) ? p.cin_off + c * 64 : p.cin2_off + (c - p.kc1) * 64;
           for (int j = 0; j < p.nbox; ++j)
-            tma_load_2d(sa + (size_t)j * p.box_rows * 128, &p.in_map, &a_full[as], p.cin_off + c * 64,
-                        row0 + j * p.box_rows);
+            tma_load_2d(sa + (size_t)j * p.box_rows * 128, im, &a_full[as], ch, row0 + j * p.box_rows);
         }
         __syncwarp();
         if (++as == p.a_stages) {
@@ -265,7 +269,7 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
         mbar_wait(&a_full[as], aph);
         tc_fence_after();
         if (half == 0 && tile == (int)blockIdx.x && c == 0) DBG_T(2);
-        const int nk = (c == p.k_chunks - 1) ? p.last_k16 : 4;
+        const int nk = (c == p.k_chunks - 1) ? p.last_k16 : ((c == p.kc1 - 1) ? p.last1_k16 : 4);
         const uint32_t a_base = smem_base + as * p.a_stage_bytes + (uint32_t)(p.halo + half * 128) * 128;
         for (int t0 = 0; t0 < 9; t0 += p.tpb) {
           mbar_wait(&b_full[bs], bph);
@@ -423,11 +427,13 @@ __global__ void unpad_add_kernel(__nv_bfloat16* __restrict__ dst, int dst_c,
 
 using namespace b200;
 
-extern "C" int b200_conv3x3_flat(const b200_flat_desc* d, const void* x, const void* w_packed,
-                                 const float* bias, const void* res1, const void* res2,
-                                 const void* mask, void* y, b200_stream_t stream) {
-  B200_REQUIRE(d && x && w_packed && y, "b200_conv3x3_flat: null argument");
-  B200_REQUIRE(d->cin > 0 && d->cin % 16 == 0, "b200_conv3x3_flat: cin %% 16");
+extern "C" int b200_conv3x3_flat(const b200_flat_desc* d, const void* x, const void* x2,
+                                 const void* w_packed, const float* bias, const void* res1,
+                                 const void* res2, const void* mask, void* y, b200_stream_t stream) {
+  B200_REQUIRE(d && w_packed && y, "b200_conv3x3_flat: null argument");
+  B200_REQUIRE((d->cin > 0 && x) || (d->cin2 > 0 && x2), "b200_conv3x3_flat: no input");
+  B200_REQUIRE(d->cin % 16 == 0 && d->cin2 % 16 == 0, "b200_conv3x3_flat: cin %% 16");
+  B200_REQUIRE(d->cin2 == 0 || (x2 && d->cx2 % 8 == 0 && d->cin2_off % 8 == 0), "b200_conv3x3_flat: bad second input");
   B200_REQUIRE(d->cout > 0 && d->cout % 16 == 0 && d->cout <= 192, "b200_conv3x3_flat: cout %% 16, <= 192");
   B200_REQUIRE(d->cx % 8 == 0 && d->cy % 8 == 0 && d->cin_off % 8 == 0 && d->cout_off % 8 == 0,
                "b200_conv3x3_flat: channel pitches/offsets must be multiples of 8");
@@ -455,8 +461,12 @@ extern "C" int b200_conv3x3_flat(const b200_flat_desc* d, const void* x, const v
   p.a_bytes = (uint32_t)p.nbox * p.box_rows * 128;
   p.a_stage_bytes = (p.a_bytes + 1023) & ~1023u;
   p.cin_off = d->cin_off;
-  p.k_chunks = (d->cin + 63) / 64;
-  p.last_k16 = (d->cin % 64 == 0) ? 4 : (d->cin % 64) / 16;
+  p.kc1 = (d->cin + 63) / 64;
+  p.last1_k16 = (d->cin % 64 == 0) ? 4 : (d->cin % 64) / 16;
+  const int kc2 = (d->cin2 + 63) / 64;
+  p.cin2_off = d->cin2_off;
+  p.k_chunks = p.kc1 + kc2;
+  p.last_k16 = kc2 ? ((d->cin2 % 64 == 0) ? 4 : (d->cin2 % 64) / 16) : p.last1_k16;
   for (int t = 0; t < 9; ++t) {
     p.tap_shift[t] = d->tap_dy[t] * p.Wp + d->tap_dx[t];
     p.tap_w[t] = d->tap_w[t];
@@ -485,11 +495,17 @@ extern "C" int b200_conv3x3_flat(const b200_flat_desc* d, const void* x, const v
   }
   B200_REQUIRE(p.b_stages >= 2, "b200_conv3x3_flat: image too wide for the shared-memory A region (w=%d)", d->w);
   p.b_ring_off = (uint32_t)p.a_stages * p.a_stage_bytes;
-  {
+  if (d->cin > 0) {
     uint64_t dims[2] = {(uint64_t)(d->cin_off + d->cin), (uint64_t)P};
     uint64_t strides[1] = {(uint64_t)d->cx * 2};
     uint32_t box[2] = {64, (uint32_t)p.box_rows};
     if (make_tensor_map(&p.in_map, x, 2, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  if (d->cin2 > 0) {
+    uint64_t dims[2] = {(uint64_t)(d->cin2_off + d->cin2), (uint64_t)P};
+    uint64_t strides[1] = {(uint64_t)d->cx2 * 2};
+    uint32_t box[2] = {64, (uint32_t)p.box_rows};
+    if (make_tensor_map(&p.in2_map, x2, 2, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   {
     uint64_t dims[3] = {(uint64_t)d->w_cin_pad, (uint64_t)d->w_cout_pad, (uint64_t)d->w_taps};

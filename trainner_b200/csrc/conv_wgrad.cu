@@ -229,10 +229,37 @@ __global__ void pack_weights_kernel(const b200_pack_entry* __restrict__ table, i
   }
 }
 
+__global__ void pack_cat_kernel(const b200_packcat_entry* __restrict__ table) {
+  const b200_packcat_entry e = table[blockIdx.y];
+  const long long total = (long long)e.taps * e.n_rows * e.cout;
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.dst);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % e.cout);
+    const int r = (int)((i / e.cout) % e.n_rows);
+    const int t = (int)(i / ((long long)e.cout * e.n_rows));
+    const float v = e.scale * e.src[((size_t)co * e.cin + e.ci_off + r) * e.taps + t];
+    dst[((size_t)t * e.rows_pad + r) * e.cols_pad + e.col_off + co] = __float2bfloat16(v);
+  }
+}
+
 }  // namespace
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_pack_cat(const b200_packcat_entry* table_dev, int32_t count, int32_t max_elems,
+                             b200_stream_t stream) {
+  if (count <= 0) return 0;
+  B200_REQUIRE(table_dev, "b200_pack_cat: null table");
+  int bx = (max_elems + 256 * 8 - 1) / (256 * 8);
+  if (bx < 1) bx = 1;
+  if (bx > 32) bx = 32;
+  dim3 grid(bx, count);
+  pack_cat_kernel<<<grid, 256, 0, as_stream(stream)>>>(table_dev);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int b200_conv_wgrad(const b200_wgrad_desc* d, const void* x, const void* dy, float* dw,
                                float* dbias, b200_stream_t stream) {

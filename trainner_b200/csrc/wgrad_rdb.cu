@@ -1,0 +1,316 @@
+// Batched weight gradient of ALL residual dense blocks in one launch (sm_100a, tcgen05).
+//
+// Per RDB r (flat, zero-bordered layout, P = n*(h+2)*(w+2) positions):
+//   X  = B[r]            [P, 192]   inputs of conv1..conv5 (channel prefixes 64/96/128/160/192)
+//   dY = G[r][:, 64:192] [P, 128]   pre-activation gradients of conv1..conv4 (32 channels each)
+//   dO = G[r+1][:, 0:64] [P, 64]    gradient of the RDB output (conv5's dY up to the factor `a`)
+//   dW_k[co][ci][tap] = sum_m X[m + shift(tap), ci] * dYcat[m, co]     (GEMM with K = positions)
+// Both operands are consumed MN-major straight from the TMA-landed [rows][64 ch] SWIZZLE_128B tiles;
+// the three taps of one kernel row (dx = -1,0,1) share the same smem tiles through row-shifted UMMA
+// descriptors, and all five convs of the block share the X tile (the output-channel axis of the
+// GEMM is the concatenation of the five dY's), so N is 64..128 instead of 32.
+//
+// Work item = (rdb, dy, type); three item types cover exactly the needed (ci, co) blocks:
+//   T1: D[ci 0..127][3 taps x (dY1..dY4 = 128 co)]     A = X atoms 0,1 (shifted), B = dY atoms 0,1
+//   T2: D[ci 0..127][3 taps x (dO = 64 co)]             A = X atoms 0,1 (shifted), B = dO atom
+//   T3: D[co' = dY3,dY4,dO (128)][3 taps x ci 128..191] A = dY atom 1 + dO atom, B = X atom 2 (shifted)
+// fp32 accumulation in TMEM over all positions (no split-K, no atomics: every (conv, co, ci, tap)
+// element is owned by exactly one item), then `+=` into the fp32 OIHW gradient tensors.
+//
+// Reference: autograd wgrad of the 5 convs of ResidualDenseBlock_5C (RRDBNet_arch.py:130-148).
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kStages = 2;
+constexpr int kXRows = 136;                       // 128 + 2 shifted rows, rounded to 8
+constexpr uint32_t kXAtom = kXRows * 128;         // 17408 B
+constexpr uint32_t kYAtom = 128 * 128;            // 16384 B
+constexpr uint32_t kStageBytes = 2 * kXAtom + 2 * kYAtom;  // 67584 B (T1 is the largest)
+
+struct RdbItemParams {
+  const CUtensorMap* maps;     // device table: per rdb [x_map (box 64 x 136), g_map (box 64 x 128), do_map (box 64 x 128)]
+  const b200_wgrad_rdb_entry* rdbs;  // device table
+  int n_rdb, P, Wp, k_steps, total_items;
+  int nf, gc;
+};
+
+__device__ __forceinline__ void item_decode(int item, int& r, int& dy, int& type) {
+  // heaviest type first so that the static round-robin schedule balances
+  type = item % 3;
+  int q = item / 3;
+  dy = q % 3 - 1;
+  r = q / 3;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_rdb_kernel(const __grid_constant__ RdbItemParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem =
+      reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tfull_bar, tempty_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tfull_bar, 1);
+    mbar_init(&tempty_bar, 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int r, dy, type;
+      item_decode(item, r, dy, type);
+      const CUtensorMap* xm = p.maps + 3 * r;
+      const CUtensorMap* gm = xm + 1;
+      const CUtensorMap* om = xm + 2;
+      for (int ks = 0; ks < p.k_steps; ++ks) {
+        const int m0 = ks * 128;
+        const int xr = m0 + dy * p.Wp - 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* s0 = smem + (size_t)stage * kStageBytes;
+          if (type == 0) {          // X atoms 0,1 | dY atoms 0,1
+            mbar_expect_tx(&full_bar[stage], 2 * kXAtom + 2 * kYAtom);
+            tma_load_2d(s0, xm, &full_bar[stage], 0, xr);
+            tma_load_2d(s0 + kXAtom, xm, &full_bar[stage], 64, xr);
+            tma_load_2d(s0 + 2 * kXAtom, gm, &full_bar[stage], p.nf, m0);
+            tma_load_2d(s0 + 2 * kXAtom + kYAtom, gm, &full_bar[stage], p.nf + 64, m0);
+          } else if (type == 1) {   // X atoms 0,1 | dO
+            mbar_expect_tx(&full_bar[stage], 2 * kXAtom + kYAtom);
+            tma_load_2d(s0, xm, &full_bar[stage], 0, xr);
+            tma_load_2d(s0 + kXAtom, xm, &full_bar[stage], 64, xr);
+            tma_load_2d(s0 + 2 * kXAtom, om, &full_bar[stage], 0, m0);
+          } else {                  // dY atom 1 (dY3,dY4), dO | X atom 2
+            mbar_expect_tx(&full_bar[stage], 2 * kYAtom + kXAtom);
+            tma_load_2d(s0, gm, &full_bar[stage], p.nf + 64, m0);
+            tma_load_2d(s0 + kYAtom, om, &full_bar[stage], 0, m0);
+            tma_load_2d(s0 + 2 * kYAtom, xm, &full_bar[stage], 128, xr);
+          }
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int r, dy, type;
+      item_decode(item, r, dy, type);
+      const int N = (type == 0) ? 128 : 64;
+      const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+      mbar_wait(&tempty_bar, acc_phase ^ 1);
+      tc_fence_after();
+      for (int ks = 0; ks < p.k_steps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t s0 = smem_base + stage * kStageBytes;
+        if (elect_one()) {
+          // A/B bases, atom strides (LBO) and which operand carries the tap shift
+          uint32_t a_base, b_base, a_lbo, b_lbo;
+          int a_shift, b_shift;
+          if (type == 2) {
+            a_base = s0; a_lbo = kYAtom; a_shift = 0;
+            b_base = s0 + 2 * kYAtom; b_lbo = kXAtom; b_shift = 1;
+          } else {
+            a_base = s0; a_lbo = kXAtom; a_shift = 1;
+            b_base = s0 + 2 * kXAtom; b_lbo = kYAtom; b_shift = 0;
+          }
+          const uint64_t a_hi = make_smem_desc(0, a_lbo, 1024, LAYOUT_SW128, 0);
+          const uint64_t b_hi = make_smem_desc(0, b_lbo, 1024, LAYOUT_SW128, 0);
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {       // dx = t - 1 ; shifted operand starts at row (1 + dx) = t
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t a_addr = a_base + (uint32_t)((a_shift ? t : 0) + k * 16) * 128;
+              const uint32_t b_addr = b_base + (uint32_t)((b_shift ? t : 0) + k * 16) * 128;
+              const uint64_t ad = a_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
+              const uint64_t bd = b_hi | (uint64_t)((b_addr >> 4) & 0x3FFF);
+              umma_f16(tmem + t * N, ad, bd, idesc, (ks | k) != 0);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (ks == p.k_steps - 1) umma_commit(&tfull_bar);
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      acc_phase ^= 1;
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;   // accumulator row: ci (T1, T2) or concatenated co' (T3)
+    uint32_t acc_phase = 0;
+    const int nf = p.nf, gc = p.gc;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int r, dy, type;
+      item_decode(item, r, dy, type);
+      const b200_wgrad_rdb_entry e = p.rdbs[r];
+      const int N = (type == 0) ? 128 : 64;
+      mbar_wait(&tfull_bar, acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem + ((uint32_t)(quad * 32) << 16);
+      for (int t = 0; t < 3; ++t) {
+        const int tap = (dy + 1) * 3 + t;
+        for (int c0 = 0; c0 < N; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_row + t * N + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = c0 + j;
+            float* dst = nullptr;
+            float scale = 1.f;
+            if (type == 0) {            // row = ci < 128 ; col -> conv k = col/gc + 1, co = col % gc
+              const int k = col / gc, co = col - k * gc;
+              const int cin_k = nf + k * gc;
+              if (row < cin_k) dst = e.dw[k] + ((size_t)co * cin_k + row) * 9 + tap;
+            } else if (type == 1) {     // conv5: ci = row < 128, co = col
+              const int cin5 = nf + 4 * gc;
+              dst = e.dw[4] + ((size_t)col * cin5 + row) * 9 + tap;
+              scale = e.scale5;
+            } else {                    // row = co' in [dY3 | dY4 | dO], col -> ci = 128 + col
+              const int ci = 2 * nf + col;   // nf = 64: X atom 2 starts at channel 128
+              if (row >= 2 * gc) {           // dO -> conv5
+                const int cin5 = nf + 4 * gc;
+                dst = e.dw[4] + ((size_t)(row - 2 * gc) * cin5 + ci) * 9 + tap;
+                scale = e.scale5;
+              } else if (row >= gc) {        // dY4 -> conv4 (cin 160): ci < 160
+                const int cin4 = nf + 3 * gc;
+                if (ci < cin4) dst = e.dw[3] + ((size_t)(row - gc) * cin4 + ci) * 9 + tap;
+              }                              // dY3 -> conv3 has only 128 inputs: nothing here
+            }
+            if (dst) *dst += scale * __uint_as_float(v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar);
+      acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+__global__ void colsum_multi_kernel(const b200_colsum_entry* __restrict__ table) {
+  const b200_colsum_entry e = table[blockIdx.y];
+  const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(e.src);
+  // 256 threads = 8 pixel lanes x 32 channel lanes; channel groups of 32 looped
+  const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  __shared__ float red[8][33];
+  for (int cg = 0; cg < e.c; cg += 32) {
+    const int ch = cg + cl;
+    float s = 0.f;
+    if (ch < e.c)
+      for (long long pix = (long long)blockIdx.x * 8 + pl; pix < e.npix; pix += (long long)gridDim.x * 8)
+        s += __bfloat162float(src[pix * e.pitch + e.coff + ch]);
+    __syncthreads();
+    red[pl][cl] = s;
+    __syncthreads();
+    if (pl == 0 && ch < e.c) {
+      float tot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tot += red[i][cl];
+      atomicAdd(e.dst + ch, e.scale * tot);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_colsum_multi(const b200_colsum_entry* table_dev, int32_t count, b200_stream_t stream) {
+  if (count <= 0) return 0;
+  B200_REQUIRE(table_dev, "b200_colsum_multi: null table");
+  dim3 grid(32, count);
+  colsum_multi_kernel<<<grid, 256, 0, as_stream(stream)>>>(table_dev);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_wgrad_rdb_make_maps(void* maps_host, int32_t n_rdb, const void* const* x_ptrs,
+                                        const void* const* g_ptrs, const void* const* do_ptrs,
+                                        const int32_t* do_pitch, int32_t n, int32_t h, int32_t w,
+                                        int32_t c) {
+  B200_REQUIRE(maps_host && x_ptrs && g_ptrs && do_ptrs && do_pitch, "b200_wgrad_rdb_make_maps: null argument");
+  CUtensorMap* m = reinterpret_cast<CUtensorMap*>(maps_host);
+  const uint64_t P = (uint64_t)n * (h + 2) * (w + 2);
+  for (int r = 0; r < n_rdb; ++r) {
+    uint64_t dims[2] = {(uint64_t)c, P};
+    uint64_t strides[1] = {(uint64_t)c * 2};
+    uint32_t boxx[2] = {64, (uint32_t)kXRows};
+    uint32_t boxy[2] = {64, 128};
+    if (make_tensor_map(&m[3 * r], x_ptrs[r], 2, dims, strides, boxx, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (make_tensor_map(&m[3 * r + 1], g_ptrs[r], 2, dims, strides, boxy, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    uint64_t dimso[2] = {64, P};
+    uint64_t strideso[1] = {(uint64_t)do_pitch[r] * 2};
+    if (make_tensor_map(&m[3 * r + 2], do_ptrs[r], 2, dimso, strideso, boxy, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  return 0;
+}
+
+extern "C" int b200_wgrad_rdb(const void* maps_dev, const b200_wgrad_rdb_entry* entries_dev, int32_t n_rdb,
+                              int32_t n, int32_t h, int32_t w, int32_t nf, int32_t gc,
+                              b200_stream_t stream) {
+  B200_REQUIRE(maps_dev && entries_dev && n_rdb > 0, "b200_wgrad_rdb: null argument");
+  B200_REQUIRE(nf == 64 && gc == 32, "b200_wgrad_rdb: the fused RDB weight-gradient kernel is specialised for nf=64, gc=32");
+  static bool attr_set = false;
+  const int kSmemBytes = kStages * kStageBytes + 1024;
+  if (!attr_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(wgrad_rdb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  RdbItemParams p;
+  p.maps = reinterpret_cast<const CUtensorMap*>(maps_dev);
+  p.rdbs = entries_dev;
+  p.n_rdb = n_rdb;
+  const long long P = (long long)n * (h + 2) * (w + 2);
+  p.P = (int)P;
+  p.Wp = w + 2;
+  p.k_steps = (int)((P + 127) / 128);
+  p.total_items = n_rdb * 9;
+  p.nf = nf;
+  p.gc = gc;
+  const int sms = sm_count();
+  const int grid = p.total_items < sms ? p.total_items : sms;
+  wgrad_rdb_kernel<<<grid, kThreads, kSmemBytes, as_stream(stream)>>>(p);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_tensor_map_bytes(void) { return (int)sizeof(CUtensorMap); }

@@ -13,10 +13,12 @@ Backward keeps one gradient buffer per RDB (ring of 4): dgrad of conv_k accumula
 [0, nf+(k-1)gc) in the epilogue (read-modify-write), and the LAST writer of a slice applies that
 slice's LeakyReLU mask, so the slice is directly conv_{k-1}'s pre-activation gradient.
 """
+import ctypes as C
+
 import torch
 
 from . import _lib
-from ._lib import lib
+from ._lib import ColsumEntry, PackCatEntry, WgradRdbEntry, lib
 from .runtime import (ConvLayer, ContextPool, FlatGrads, Lease, LRELU_SLOPE, P, Plan, WeightPacker,
                       add_flat, add_igemm, add_wgrad, make_conv_desc, make_flat_desc, require_device, taps_conv,
                       taps_dgrad_s1)
@@ -47,7 +49,35 @@ class RRDBNetEngine:
         self.ups = [ConvLayer(c, "upconv%d" % i) for i, c in enumerate(k["ups"])]
         self.hr0 = ConvLayer(k["hr0"], "HR_conv0")
         self.tc_layers = [l for r in self.rdbs for l in r] + [self.lr] + self.ups + [self.hr0]
-        self.packer = WeightPacker(self.tc_layers, device)
+        # RDB input gradients use the GATHER form: for each channel slice s of the block's buffer
+        # (x, x1..x4) ONE conv over the concatenated pre-activation gradients of all later convs,
+        # instead of 5 read-modify-write dgrads (profiles/r01_flat_v0_timeline.txt: the RMW epilogue
+        # dominated).  Wcat[r][s] : [9 taps][N_s rows = slice channels][K = dY_{s+1..4} | dO] bf16.
+        nf, gc = net.nf, net.gc
+        cat_entries = []
+        self.wcat = []
+        for r, convs in enumerate(self.rdbs):
+            for l in convs:
+                l.need_dgrad = False
+            a = 0.04 if r % 3 == 2 else 0.2
+            per_slice = []
+            for sl in range(5):
+                n_s = nf if sl == 0 else gc
+                lo = 0 if sl == 0 else nf + (sl - 1) * gc
+                k1 = (4 - sl) * gc
+                k1p = (k1 + 63) // 64 * 64
+                cols = k1p + nf
+                wt = torch.zeros(9, n_s, cols, dtype=BF16, device=device)
+                for kk in range(sl, 4):       # convs sl+1..4 (index kk), dY at G channels [nf+kk*gc, +gc)
+                    cv = convs[kk]
+                    cat_entries.append(PackCatEntry(cv.weight.data_ptr(), wt.data_ptr(), gc, cv.cin, 9, lo, n_s, n_s,
+                                                    cols, (kk - sl) * gc, 1.0, 0))
+                cv = convs[4]
+                cat_entries.append(PackCatEntry(cv.weight.data_ptr(), wt.data_ptr(), nf, cv.cin, 9, lo, n_s, n_s, cols,
+                                                k1p, a, 0))
+                per_slice.append((wt, n_s, lo, k1, cols))
+            self.wcat.append(per_slice)
+        self.packer = WeightPacker(self.tc_layers, device, cat_entries)
         self.grads = FlatGrads(list(net.parameters()), device)
         self.pools = {}
 
@@ -132,7 +162,7 @@ class RRDBNetEngine:
     def _make_backward(self, ctx):
         net = self.net
         nf, gc = net.nf, net.gc
-        C = nf + 4 * gc
+        CC = nf + 4 * gc
         N, h, w = ctx.shape
         H, W = ctx.HW
         dev = self.device
@@ -144,7 +174,9 @@ class RRDBNetEngine:
         ctx.dV = e(N, H, W, nf)
         ctx.dU = [e(*u.shape) for u in ctx.U]
         ctx.dP = [e(u.shape[0], u.shape[1] // 2, u.shape[2] // 2, nf) for u in ctx.U]
-        ctx.G = [torch.zeros(N, h + 2, w + 2, C, dtype=BF16, device=dev) for _ in range(4)]  # flat
+        # one flat gradient buffer per RDB (kept until the batched weight-gradient kernel has run:
+        # 70 x 27 MB at config 2 -- HBM is 180 GB, launch count and atomics are the scarce resource)
+        ctx.G = [torch.zeros(N, h + 2, w + 2, CC, dtype=BF16, device=dev) for _ in range(nrdb + 1)]
         ctx.dFea = e(N, h, w, nf)
         Hp, Wp = h + 2, w + 2
         b = Plan()
@@ -176,10 +208,10 @@ class RRDBNetEngine:
                   ww, nf, SL)
             dcur = ctx.dP[i]
         dT = dcur  # gradient wrt (fea + LR_conv(trunk)) at LR resolution
-        slot = lambda r: ctx.G[r % 4]
+        slot = lambda r: ctx.G[r]
         L = self.lr
         # dT is dense [N,h,w,nf]; its dgrad lands in the interior of the flat gradient buffer
-        d = make_conv_desc(N, h, w, nf, 0, nf, h, w, Hp, Wp, C, 0, nf, taps_dgrad_s1(3, 1), L.taps, L.dgr_rows,
+        d = make_conv_desc(N, h, w, nf, 0, nf, h, w, Hp, Wp, CC, 0, nf, taps_dgrad_s1(3, 1), L.taps, L.dgr_rows,
                            L.dgr_cols, out_off=(1, 1))
         add_igemm(b, d, dT, L.w_dgr, y=slot(nrdb))
         # x flat (its own border is the conv's zero padding -> pad 0 on the flat grid), dy dense
@@ -191,25 +223,53 @@ class RRDBNetEngine:
             first_of_rrdb = (r % 3 == 0)
             a = 0.04 if last_of_rrdb else 0.2
             b1 = 0.2 if last_of_rrdb else 1.0
-            L = convs[4]
-            d = make_flat_desc(N, h, w, C, 0, nf, C, 0, C, taps_dgrad_s1(3, 1), L.taps, L.dgr_rows, L.dgr_cols,
-                               alpha=a, beta1=b1, res_nch=nf, res1_c=C, res1_coff=0,
-                               beta2=1.0 if first_of_rrdb else 0.0, res2_c=C, res2_coff=0, mask_c=C, mask_coff=0,
-                               mask_lo=nf + 3 * gc, mask_hi=C, mask_slope=SL)
-            add_flat(b, d, dO, L.w_dgr, res1=dO, res2=slot(r + 3) if first_of_rrdb else None, mask=Br, y=Gr)
-            # wgrads run on the whole flat grid: the zero borders of x and dy contribute nothing
-            add_wgrad(b, N, Hp, Wp, C, 0, C, Hp, Wp, C, 0, nf, 3, 1, 1, a, Br, dO, g(L.weight), g(L.bias))
-            for kk in range(3, -1, -1):
-                L = convs[kk]
-                lo = nf + kk * gc  # this conv's output slice [lo, lo+gc) == its dY; inputs are [0, lo)
-                d = make_flat_desc(N, h, w, C, lo, gc, C, 0, lo, taps_dgrad_s1(3, 1), L.taps, L.dgr_rows, L.dgr_cols,
-                                   accumulate=1, mask_c=C, mask_coff=0, mask_lo=lo - gc if kk > 0 else 0,
-                                   mask_hi=lo if kk > 0 else 0, mask_slope=SL)
-                add_flat(b, d, Gr, L.w_dgr, mask=Br if kk > 0 else None, y=Gr)
-                add_wgrad(b, N, Hp, Wp, C, 0, lo, Hp, Wp, C, lo, gc, 3, 1, 1, 1.0, Br, Gr, g(L.weight), g(L.bias))
+            for sl in range(4, -1, -1):
+                wt, n_s, lo, k1, cols = self.wcat[r][sl]
+                kw = dict(cx2=CC, cin2_off=0, cin2=nf)
+                if sl == 0:
+                    kw.update(beta1=b1, res_nch=nf, res1_c=CC, res1_coff=0, beta2=1.0 if first_of_rrdb else 0.0,
+                              res2_c=CC, res2_coff=0)
+                else:
+                    kw.update(mask_c=CC, mask_coff=lo, mask_lo=0, mask_hi=n_s, mask_slope=SL)
+                d = make_flat_desc(N, h, w, CC, nf + sl * gc, k1, CC, lo, n_s, taps_dgrad_s1(3, 1), 9, n_s, cols, **kw)
+                add_flat(b, d, Gr if k1 else None, wt, x2=dO,
+                         res1=dO if sl == 0 else None,
+                         res2=slot(r + 3) if (sl == 0 and first_of_rrdb) else None,
+                         mask=Br if sl > 0 else None, y=Gr)
+        # ---- weight / bias gradients of all RDB convs: ONE batched tcgen05 kernel + one column-sum kernel
+        P_pos = N * Hp * Wp
+        tmb = lib.b200_tensor_map_bytes()
+        maps_host = torch.empty(3 * nrdb * tmb + 64, dtype=torch.uint8)
+        base = (maps_host.data_ptr() + 63) // 64 * 64
+        vp = lambda xs: (C.c_void_p * len(xs))(*xs)
+        pitches = (C.c_int32 * nrdb)(*([CC] * nrdb))
+        _lib.check(lib.b200_wgrad_rdb_make_maps(base, nrdb, vp([ctx.B[r].data_ptr() for r in range(nrdb)]),
+                                                vp([ctx.G[r].data_ptr() for r in range(nrdb)]),
+                                                vp([ctx.G[r + 1].data_ptr() for r in range(nrdb)]), pitches,
+                                                N, h, w, CC), "wgrad_rdb_make_maps")
+        off = base - maps_host.data_ptr()
+        ctx.wg_maps = maps_host[off:off + 3 * nrdb * tmb].clone().to(dev)
+        entries, sums = [], []
+        for r, convs in enumerate(self.rdbs):
+            a = 0.04 if r % 3 == 2 else 0.2
+            e = WgradRdbEntry()
+            for kk in range(5):
+                e.dw[kk] = g(convs[kk].weight).data_ptr()
+            e.scale5 = a
+            entries.append(e)
+            for kk in range(4):
+                sums.append(ColsumEntry(ctx.G[r].data_ptr(), g(convs[kk].bias).data_ptr(), P_pos, CC, nf + kk * gc, gc, 1.0))
+            sums.append(ColsumEntry(ctx.G[r + 1].data_ptr(), g(convs[4].bias).data_ptr(), P_pos, CC, 0, nf, a))
+        to_dev = lambda arr: torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        ctx.wg_entries = to_dev((WgradRdbEntry * len(entries))(*entries))
+        ctx.wg_sums = to_dev((ColsumEntry * len(sums))(*sums))
+        b.add(lib.b200_wgrad_rdb, P(ctx.wg_maps), P(ctx.wg_entries), nrdb, N, h, w, nf, gc,
+              flops=2.0 * N * h * w * 9 * nrdb * (nf * gc + (nf + gc) * gc + (nf + 2 * gc) * gc + (nf + 3 * gc) * gc + CC * nf),
+              tag="wgrad_rdb", info="%d RDBs" % nrdb)
+        b.add(lib.b200_colsum_multi, P(ctx.wg_sums), len(sums))
         # shortcut: d(fea) = interior(G[0][0:nf]) + dT  (dense), then the thin conv's weight gradient
         G0 = slot(0)
-        b.add(lib.b200_unpad_add, P(ctx.dFea), nf, P(G0), C, 0, P(dT), nf, N, h, w, nf)
+        b.add(lib.b200_unpad_add, P(ctx.dFea), nf, P(G0), CC, 0, P(dT), nf, N, h, w, nf)
         b.add(lib.b200_conv3x3_thin_wgrad, P(ctx.x), P(ctx.dFea), P(g(self.fea.weight)), P(g(self.fea.bias)), None,
               N, h, w, net.in_nc, nf, nf, 0, 1, None, None)
         ctx.bwd = b

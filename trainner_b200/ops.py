@@ -259,6 +259,6 @@ def conv3x3_flat(x_flat, w_oihw, bias=None, dgrad=False, cin_off=0, out=None, co
                        accumulate=1 if accumulate else 0, mask_c=mask.shape[3] if mask is not None else 0,
                        mask_coff=mask_coff, mask_lo=mask_lo, mask_hi=mask_hi, mask_slope=mask_slope)
     b = bias.detach().float().contiguous() if bias is not None else None
-    _lib.check(lib.b200_conv3x3_flat(C.byref(d), _p(x_flat), _p(wp), _p(b), _p(res1), _p(res2), _p(mask), _p(out),
+    _lib.check(lib.b200_conv3x3_flat(C.byref(d), _p(x_flat), None, _p(wp), _p(b), _p(res1), _p(res2), _p(mask), _p(out),
                                      stream_ptr()), "conv3x3_flat")
     return out

@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, FlatDesc, PackEntry, WgradDesc, lib
+from ._lib import ConvDesc, FlatDesc, PackCatEntry, PackEntry, WgradDesc, lib
 
 LRELU_SLOPE = 0.2
 
@@ -130,8 +130,14 @@ class WeightPacker:
     """Repacks every tensor-core conv weight of a network with ONE kernel launch, only when a
     parameter changed (tracked through Tensor._version)."""
 
-    def __init__(self, layers, device):
+    def __init__(self, layers, device, cat_entries=None):
         self.layers = layers
+        self.cat_count = 0
+        if cat_entries:
+            self.cat_count = len(cat_entries)
+            arr = (PackCatEntry * self.cat_count)(*cat_entries)
+            self.cat_table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+            self.cat_max = max(e.taps * e.n_rows * e.cout for e in cat_entries)
         entries = []
         for l in layers:
             l.alloc(device)
@@ -170,6 +176,9 @@ class WeightPacker:
         if need:
             _lib.check(lib.b200_pack_weights(self.table.data_ptr(), self.count, self.max_elems,
                                              stream_ptr()), "pack_weights")
+            if self.cat_count:
+                _lib.check(lib.b200_pack_cat(self.cat_table.data_ptr(), self.cat_count, self.cat_max,
+                                             stream_ptr()), "pack_cat")
             self.version = ver
             self.dirty = False
 
@@ -312,11 +321,13 @@ def add_wgrad(plan, n, h_in, w_in, cx, x_coff, cin, h_out, w_out, cdy, dy_coff, 
 
 
 def make_flat_desc(n, h, w, cx, cin_off, cin, cy, cout_off, cout, taps, w_taps, w_rows, w_cols, out_mode=0,
+                   cx2=0, cin2_off=0, cin2=0,
                    alpha=1.0, act=0, slope=0.0, beta1=0.0, beta2=0.0, res_nch=0, res1_c=0, res1_coff=0,
                    res2_c=0, res2_coff=0, accumulate=0, mask_c=0, mask_coff=0, mask_lo=0, mask_hi=0,
                    mask_slope=0.0):
     d = FlatDesc()
     d.n, d.h, d.w, d.cx, d.cin_off, d.cin, d.cy, d.cout_off, d.cout = n, h, w, cx, cin_off, cin, cy, cout_off, cout
+    d.cx2, d.cin2_off, d.cin2 = cx2, cin2_off, cin2
     assert len(taps) == 9
     for i, (dy, dx, wi) in enumerate(taps):
         d.tap_dy[i], d.tap_dx[i], d.tap_w[i] = dy, dx, wi
@@ -329,9 +340,10 @@ def make_flat_desc(n, h, w, cx, cin_off, cin, cy, cout_off, cout, taps, w_taps, 
     return d
 
 
-def add_flat(plan, desc, x, w, bias=None, res1=None, res2=None, mask=None, y=None):
+def add_flat(plan, desc, x, w, bias=None, res1=None, res2=None, mask=None, y=None, x2=None):
     plan.keep(desc)
-    flops = 2.0 * desc.n * desc.h * desc.w * desc.cout * desc.cin * 9
-    info = "cin%d cout%d %dx%dx%d%s" % (desc.cin, desc.cout, desc.n, desc.h, desc.w, " acc" if desc.accumulate else "")
-    plan.add(lib.b200_conv3x3_flat, C.byref(desc), P(x), P(w), P(bias), P(res1), P(res2), P(mask), P(y),
+    flops = 2.0 * desc.n * desc.h * desc.w * desc.cout * (desc.cin + desc.cin2) * 9
+    info = "cin%d+%d cout%d %dx%dx%d%s" % (desc.cin, desc.cin2, desc.cout, desc.n, desc.h, desc.w,
+                                          " acc" if desc.accumulate else "")
+    plan.add(lib.b200_conv3x3_flat, C.byref(desc), P(x), P(x2), P(w), P(bias), P(res1), P(res2), P(mask), P(y),
              flops=flops, tag="conv_flat", info=info)
