@@ -39,7 +39,9 @@ struct IgemmParams {
   int ntaps;
   int8_t tap_dy[B200_MAX_TAPS], tap_dx[B200_MAX_TAPS], tap_w[B200_MAX_TAPS];
   int BN, Cout;
-  int acc_cols;  // TMEM column stride between the two accumulator buffers
+  int acc_cols;  // TMEM column stride between accumulator buffers
+  int acc_stages;  // 256-row kernel: 2 when 4 * acc_cols <= 512, else 1
+  uint32_t a_bytes;  // bytes of one A slot (128 or 256 pixel rows x 128 B)
   int stages;
   uint32_t b_bytes;  // BN * 128 (TMA transaction bytes of one B slot)
   uint32_t stage_bytes;
@@ -307,6 +309,255 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// 256-row variant: the tile is 256 output pixels (two 128-row MMA tiles sharing every weight slot),
+// two MMA-issuing warps (one thread sustains only ~1 tcgen05.mma / 49 cycles plus ~300 cycles of
+// barrier round trip per k-iteration -- profiles/r01_flat_v0_timeline.txt), 8 epilogue warps that
+// request all their global operands before waiting on the TMEM load.  Used whenever the layer has
+// enough 256-pixel tiles to fill the SMs; the 128-row kernel above serves the small layers.
+constexpr int kThreads256 = 352;
+
+template <int NC>
+struct EpiLoads256 {
+  uint4 a[NC / 8];   // previous output (accumulate) or residual 1
+  uint4 r2[NC / 8];
+  uint4 msk[NC / 8];
+};
+
+template <int NC>
+__device__ __forceinline__ void epi256_load(const IgemmParams& p, EpiLoads256<NC>& L, int cbase, long long pix_lin,
+                                            const __nv_bfloat16* out_px) {
+#pragma unroll
+  for (int g = 0; g < NC / 8; ++g) {
+    const int c = cbase + g * 8;
+    if (c >= p.Cout) break;
+    if (p.accumulate) L.a[g] = *reinterpret_cast<const uint4*>(out_px + p.o_coff + c);
+    if (p.mask && c >= p.mask_lo && c < p.mask_hi)
+      L.msk[g] = __ldg(reinterpret_cast<const uint4*>(p.mask + pix_lin * p.mask_c + p.mask_coff + c));
+    if (c < p.res_nch) {
+      if (p.res1) L.a[g] = __ldg(reinterpret_cast<const uint4*>(p.res1 + pix_lin * p.res1_c + p.res1_coff + c));
+      if (p.res2) L.r2[g] = __ldg(reinterpret_cast<const uint4*>(p.res2 + pix_lin * p.res2_c + p.res2_coff + c));
+    }
+  }
+}
+
+template <int NC>
+__device__ __forceinline__ void epi256_store(const IgemmParams& p, const uint32_t* acc, const EpiLoads256<NC>& L,
+                                             int cbase, __nv_bfloat16* out_px) {
+#pragma unroll
+  for (int g = 0; g < NC / 8; ++g) {
+    const int c = cbase + g * 8;
+    if (c >= p.Cout) break;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
+    if (p.bias) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
+    if (c < p.res_nch) {
+      if (p.res1) {
+        float r[8];
+        unpack8(L.a[g], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(p.beta1, r[j], v[j]);
+      }
+      if (p.res2) {
+        float r[8];
+        unpack8(L.r2[g], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(p.beta2, r[j], v[j]);
+      }
+    }
+    __nv_bfloat16* dst = out_px + p.o_coff + c;
+    if (p.accumulate) {
+      float r[8];
+      unpack8(L.a[g], r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    if (p.act) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+    }
+    if (p.mask && c >= p.mask_lo && c < p.mask_hi) {
+      float r[8];
+      unpack8(L.msk[g], r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = r[j] > 0.f ? v[j] : v[j] * p.mask_slope;
+    }
+    const uint4 o = pack8(v);
+    *reinterpret_cast<uint4*>(dst) = o;
+    if (p.upsample) {
+      *reinterpret_cast<uint4*>(dst + p.o_sx) = o;
+      *reinterpret_cast<uint4*>(dst + p.o_sy) = o;
+      *reinterpret_cast<uint4*>(dst + p.o_sy + p.o_sx) = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads256, 1)
+conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem =
+      reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 2);
+    }
+    mbar_init(&tfull_bar[0], 2);
+    mbar_init(&tfull_bar[1], 2);
+    mbar_init(&tempty_bar[0], 8);
+    mbar_init(&tempty_bar[1], 8);
+    mbar_fence_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.in_map);
+    tma_prefetch_desc(&p.w_map);
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int k_iters = p.ntaps * p.k_chunks;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      for (int t = 0; t < p.ntaps; ++t) {
+        const int cx = tc.x0 * p.in_stride + p.in_off_x + p.tap_dx[t];
+        const int cy = tc.y0 * p.in_stride + p.in_off_y + p.tap_dy[t];
+        const int wt = p.tap_w[t];
+        for (int c = 0; c < p.k_chunks; ++c) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
+            uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+            mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+            tma_load_4d(sa, &p.in_map, &full_bar[stage], p.cin_off + c * 64, cx, cy, tc.n0);
+            tma_load_3d(sa + p.a_bytes, &p.w_map, &full_bar[stage], c * 64, tc.nb * p.BN, wt);
+          }
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    const int half = warp - 1;
+    const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
+    const uint64_t desc_hi = make_smem_desc(0, 16, 1024, LAYOUT_SW128, 0);
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem + acc * 2 * p.acc_cols + half * p.acc_cols;
+      int c = 0;
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const int nk = (c == p.k_chunks - 1) ? p.last_k16 : 4;
+        const uint32_t a_addr = smem_base + stage * p.stage_bytes + half * kABytes;
+        const uint32_t b_addr = smem_base + stage * p.stage_bytes + p.a_bytes;
+        if (elect_one()) {
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t ad = desc_hi | (uint64_t)(((a_addr + k * 32) >> 4) & 0x3FFF);
+            const uint64_t bd = desc_hi | (uint64_t)(((b_addr + k * 32) >> 4) & 0x3FFF);
+            umma_f16(d_tmem, ad, bd, idesc, (it | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++c == p.k_chunks) c = 0;
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (p.acc_stages == 2) {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      } else {
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int half = (warp - 3) >> 2;
+    const int m = half * 128 + quad * 32 + lane;
+    const int ix = m % p.tw;
+    const int iy = (m / p.tw) % p.th;
+    const int in_ = m / (p.tw * p.th);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int x = tc.x0 + ix, y = tc.y0 + iy, n = tc.n0 + in_;
+      const bool valid = (x < p.Wo) && (y < p.Ho) && (n < p.Nimg);
+      const long long pix_lin = ((long long)n * p.aux_h + (y * p.aux_my + p.aux_oy)) * p.aux_w +
+                                (x * p.aux_mx + p.aux_ox);
+      __nv_bfloat16* out_px = p.out + (long long)n * p.o_sn +
+                              (long long)(y * p.o_my + p.o_oy) * p.o_sy +
+                              (long long)(x * p.o_mx + p.o_ox) * p.o_sx;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem + ((uint32_t)(quad * 32) << 16) + acc * 2 * p.acc_cols + half * p.acc_cols;
+      const int cb = tc.nb * p.BN;
+      int c0 = 0;
+      for (; c0 + 32 <= p.BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c0, r);
+        EpiLoads256<32> L;
+        if (valid) epi256_load<32>(p, L, cb + c0, pix_lin, out_px);
+        tmem_ld_wait();
+        if (valid) epi256_store<32>(p, r, L, cb + c0, out_px);
+      }
+      if (c0 < p.BN) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_row + c0, r);
+        EpiLoads256<16> L;
+        if (valid) epi256_load<16>(p, L, cb + c0, pix_lin, out_px);
+        tmem_ld_wait();
+        if (valid) epi256_store<16>(p, r, L, cb + c0, out_px);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (p.acc_stages == 2) {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      } else {
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 inline int pow2_ceil(int v) {
   int r = 1;
   while (r < v) r <<= 1;
@@ -338,28 +589,42 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
   if (!attr_set) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm256_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
 
   IgemmParams p;
   memset(&p, 0, sizeof(p));
-  // ---- tile geometry
-  p.tw = d->w_out > 8 ? 16 : (d->w_out > 4 ? 8 : 4);
-  int th_max = 128 / p.tw;
-  p.th = pow2_ceil(d->h_out) < th_max ? pow2_ceil(d->h_out) : th_max;
-  p.tn = 128 / (p.tw * p.th);
-  p.tiles_x = (d->w_out + p.tw - 1) / p.tw;
-  p.tiles_y = (d->h_out + p.th - 1) / p.th;
-  p.tiles_n = (d->n + p.tn - 1) / p.tn;
-  const int pixel_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-  // ---- N tile
-  int BN = d->cout <= 256 ? ((d->cout + 15) / 16) * 16 : 256;
-  auto nblocks = [&](int bn) { return (d->cout + bn - 1) / bn; };
+  // ---- tile geometry: 256-pixel tiles (two MMA issuers) when the layer has enough of them
   const int sms = sm_count();
-  while (BN >= 128 && BN % 32 == 0 && d->cout % (BN / 2) == 0 && pixel_tiles * nblocks(BN) < sms)
-    BN /= 2;
+  auto geometry = [&](int rows) {
+    p.tw = d->w_out > 8 ? 16 : (d->w_out > 4 ? 8 : 4);
+    int th_max = rows / p.tw;
+    p.th = pow2_ceil(d->h_out) < th_max ? pow2_ceil(d->h_out) : th_max;
+    p.tn = rows / (p.tw * p.th);
+    p.tiles_x = (d->w_out + p.tw - 1) / p.tw;
+    p.tiles_y = (d->h_out + p.th - 1) / p.th;
+    p.tiles_n = (d->n + p.tn - 1) / p.tn;
+    return p.tiles_x * p.tiles_y * p.tiles_n;
+  };
+  auto nblocks = [&](int bn) { return (d->cout + bn - 1) / bn; };
+  int BN = d->cout <= 256 ? ((d->cout + 15) / 16) * 16 : 256;
+  int pixel_tiles = geometry(256);
+  int bn256 = BN;
+  while (bn256 >= 128 && bn256 % 32 == 0 && d->cout % (bn256 / 2) == 0 && pixel_tiles * nblocks(bn256) < sms)
+    bn256 /= 2;
+  const bool use256 = pixel_tiles * nblocks(bn256) >= (sms * 3) / 4;
+  if (use256) {
+    BN = bn256;
+  } else {
+    pixel_tiles = geometry(128);
+    while (BN >= 128 && BN % 32 == 0 && d->cout % (BN / 2) == 0 && pixel_tiles * nblocks(BN) < sms) BN /= 2;
+  }
   p.BN = BN;
   p.acc_cols = (BN + 31) & ~31;
+  p.acc_stages = (4 * p.acc_cols <= 512) ? 2 : 1;
+  p.a_bytes = use256 ? 2 * kABytes : kABytes;
   p.n_blocks = nblocks(BN);
   p.total_tiles = pixel_tiles * p.n_blocks;
   p.Nimg = d->n;
@@ -380,7 +645,7 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
   }
   p.Cout = d->cout;
   p.b_bytes = (uint32_t)BN * 128;
-  p.stage_bytes = kABytes + ((p.b_bytes + 1023) & ~1023u);
+  p.stage_bytes = p.a_bytes + ((p.b_bytes + 1023) & ~1023u);
   p.stages = (kSmemBytes - 2048) / (int)p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   B200_REQUIRE(p.stages >= 2, "b200_conv_igemm: not enough shared memory for 2 stages");
@@ -446,7 +711,10 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
 
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-  conv_igemm_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(p);
+  if (use256)
+    conv_igemm256_kernel<<<grid, kThreads256, smem, as_stream(stream)>>>(p);
+  else
+    conv_igemm_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(p);
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -26,6 +26,12 @@ class DiscriminatorEngine:
         self.net = net
         self.device = None
         self.pools = {}
+        # Forward reuse: within one generation of the weights, D(x) of the SAME input tensor is
+        # value-identical, so the second call (D-step after G-step: losses.py:400-403 vs :475-476)
+        # only repeats the BatchNorm running-stat update.  Off by default; the owner of the
+        # optimizer (models/sr_model.py) switches it on.
+        self.reuse = False
+        self._cache = {}
 
     def _setup(self, device):
         net = self.net
@@ -94,6 +100,11 @@ class DiscriminatorEngine:
 
         ctx.fwd_train = fwd_plan(True)
         ctx.fwd_eval = fwd_plan(False)
+        rf = Plan()   # the running-stat side effect of a train-mode forward, replayed on forward reuse
+        for i, (L, bn) in enumerate(self.layers):
+            rf.add(lib.b200_bn_finalize, P(ctx.stats[i]), P(ctx.mi[i]), P(bn.running_mean), P(bn.running_var),
+                   N * ctx.dims[i][1] * ctx.dims[i][1], L.cout, float(bn.momentum), float(bn.eps))
+        ctx.refinalize = rf
         ctx.bwd = {}
         return ctx
 
@@ -161,8 +172,26 @@ class DiscriminatorEngine:
         if key not in self.pools:
             self.pools[key] = ContextPool(lambda: self._make_context(N, S))
         pool = self.pools[key]
-        ctx = pool.acquire()
         self.packer.ensure()
+        ckey = (x.data_ptr(), x._version, tuple(x.shape))
+        if self.reuse and training:
+            hit = self._cache.get(ckey)
+            if hit is not None and hit[1] == self.packer.pack_count and hit[0] in pool.free:
+                ctx = hit[0]
+                pool.free.remove(ctx)
+                ctx.refinalize.run()
+                for _, bn in self.layers:
+                    bn.num_batches_tracked.add_(1)
+                feat = ctx.feat.clone()
+                if need_backward:
+                    return feat, Lease(pool, ctx)
+                pool.release(ctx)
+                return feat, None
+        ctx = pool.acquire()
+        for k in [k for k, v in self._cache.items() if v[0] is ctx]:
+            del self._cache[k]
+        if self.reuse and training:
+            self._cache[ckey] = (ctx, self.packer.pack_count)
         ctx.x.copy_(x)
         ctx.trained = bool(training)
         if training:

@@ -85,6 +85,8 @@ class SRModel:
             if getattr(e, "packer", None) is not None:
                 e.packer.explicit = True
                 e.packer.mark_dirty()
+            if hasattr(e, "reuse"):
+                e.reuse = True   # D(fake) / D(real) of the G step are reused by the D step
 
     # ------------------------------------------------------------------ reference-facing API
     def feed_data(self, data, need_HR=True):

@@ -150,6 +150,7 @@ class WeightPacker:
             self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
             self.max_elems = max(e.taps * e.rows_pad * e.cols_pad for e in entries)
         self.version = None
+        self.pack_count = 0
         self.dirty = True
         self.explicit = False
         self.was_trainable = False
@@ -181,6 +182,7 @@ class WeightPacker:
                                              stream_ptr()), "pack_cat")
             self.version = ver
             self.dirty = False
+            self.pack_count += 1
 
 
 class FlatGrads:
