@@ -331,12 +331,14 @@ __global__ void l1_loss_kernel(const T* __restrict__ a, const T* __restrict__ b,
 // ------------------------------------------------------------------ layout conversion
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n,
                                     int c, int h, int w, int cy, int coff) {
-  const long long total = (long long)n * h * w;
+  const long long hw = (long long)h * w;
+  const long long total = (long long)n * hw * c;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const long long b = i / ((long long)h * w), hw = i % ((long long)h * w);
-    for (int ch = 0; ch < c; ++ch)
-      y[i * cy + coff + ch] = __float2bfloat16(x[(b * c + ch) * h * w + hw]);
+    const int ch = (int)(i % c);
+    const long long pix = i / c;
+    const long long b = pix / hw, p = pix % hw;
+    y[pix * cy + coff + ch] = __float2bfloat16(x[(b * c + ch) * hw + p]);
   }
 }
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int n,
@@ -508,7 +510,7 @@ int b200_lrelu_mask_mul(const void* g, const void* y, void* out, int64_t numel, 
 
 int b200_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t h, int32_t w,
                                int32_t cy, int32_t y_coff, b200_stream_t stream) {
-  nchw_to_nhwc_kernel<<<grid_for((long long)n * h * w, 256), 256, 0, as_stream(stream)>>>(
+  nchw_to_nhwc_kernel<<<grid_for((long long)n * h * w * c, 256), 256, 0, as_stream(stream)>>>(
       x, (bf16*)y, n, c, h, w, cy, y_coff);
   B200_LAUNCH_CHECK();
   return 0;
