@@ -283,7 +283,7 @@ def main():
     # ---- roofline leg: one instrumented step, CUDA events around every kernel launch of the plans
     roof = None
     cpu_base = None
-    if rank == 0:
+    if True:  # every rank runs the instrumented step (it contains the gradient all-reduce); rank 0 reports
         from trainner_b200 import runtime
         rows = []
         orig_run = runtime.Plan.run
@@ -299,7 +299,7 @@ def main():
         finally:
             runtime.Plan.run = orig_run
             runtime.Plan.detail_sink = None
-        if detail is not None:
+        if detail is not None and rank == 0:
             grp = {}
             for tag, info, t_ms, fl in detail:
                 a = grp.setdefault((tag, info), [0, 0.0, 0.0])
@@ -328,7 +328,7 @@ def main():
                                for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
                 "step_algorithmic_tflops": GFLOP_PER_IMAGE_STEP * 1e-3 * args.batch,
                 "step_frac_of_peak": (GFLOP_PER_IMAGE_STEP * 1e9 * (args.batch / (ms / 1e3))) / (peak * 1e12)}
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and rank == 0:
             c_ips, c_dt, threads = cpu_reference_steps(args, 2, 1)
             cpu_base = {"value": c_ips * px, "unit": "HR-px/s", "images_per_sec": c_ips, "cores": threads,
                         "kind": "port", "sample": "2 timed steps at batch 1 (nb=%d, HR %d^2), fp32" % (args.nb, args.hr)}
