@@ -105,6 +105,34 @@ int b200_unpad_add(void* dst_dense, int32_t dst_c, const void* src_flat, int32_t
                    const void* add_dense, int32_t add_c, int32_t n, int32_t h, int32_t w, int32_t c,
                    b200_stream_t stream);
 
+/* TMEM-persistent, stage-merged residual dense block (csrc/rdb_persist.cu): one launch computes the
+ * whole block -- forward, or its input gradient in gather form.  Stage j consumes one 64/32-channel
+ * input slice and accumulates into all not-yet-complete output columns (192 - 32 j of them, fp32 in
+ * TMEM for the whole block); the 32 (last stage 64) columns completed by stage j are finished with
+ * the stage's epilogue and written to `out`, which is the next stage's input.
+ * w_packed: bf16 [9 taps][192 - 32 j rows][64 cols] (b200_pack_cat).  All tensors flat
+ * [n, h+2, w+2, c]; n*(h+2)*(w+2) <= 256 * #SMs (one tile per CTA, cooperative launch).
+ * flags: zero-initialised int array of >= #tiles; flag_base must grow by >= 8 per launch.       */
+typedef struct {
+  const void* x; int32_t cx, cin_off, cin;       /* input slice (cin = 64 or 32)                */
+  const void* w_packed;
+  void* out; int32_t out_c, out_coff;             /* completing slice                            */
+  const float* bias;                              /* [32] ([64] for the last stage) or NULL     */
+  const void* mask; int32_t mask_c, mask_coff;    /* v *= lrelu'(mask) with mask_slope          */
+  const void* res1; int32_t res1_c, res1_coff;
+  const void* res2; int32_t res2_c, res2_coff;
+  float alpha, beta1, beta2, slope, mask_slope;   /* v = alpha*(acc+bias) + beta1*res1 + beta2*res2 -> lrelu(slope) if act */
+  int32_t act;
+} b200_rdb_stage;
+
+typedef struct {
+  int32_t n, h, w;
+  int32_t flip_taps;   /* 0: input offset of weight tap (ky,kx) is (ky-1, kx-1) (forward); 1: (1-ky, 1-kx) (input gradient) */
+  b200_rdb_stage stage[5];
+} b200_rdb_desc;
+
+int b200_rdb_persist(const b200_rdb_desc* d, int32_t* flags, int32_t flag_base, b200_stream_t stream);
+
 /* Weight gradient of a conv (autograd wgrad of block.py:238):
  *   dw[co][ci][ky][kx] += scale * sum_{n,y,x} dy[n,y,x,dy_coff+co] * x[n, y*stride+ky-pad, x*stride+kx-pad, x_coff+ci]
  * dw is fp32 OIHW (the layout of nn.Conv2d.weight.grad); accumulated with fp32 atomics.      */
@@ -168,8 +196,12 @@ typedef struct {
   void* dst;
   int32_t cout, cin, taps, ci_off, n_rows, rows_pad, cols_pad, col_off;
   float scale;
+  int32_t row_off;  /* destination row offset */
+  int32_t mode;     /* 1 (default 0 means 1 for backward compatibility is NOT applied): see below */
   int32_t pad_;
 } b200_packcat_entry;
+/* mode 1: rows = input channels : dst[t][row_off + r][col_off + co] = scale*src[co][ci_off + r][t], r < n_rows
+ * mode 0: rows = output channels: dst[t][row_off + co][col_off + c] = scale*src[co][ci_off + c][t], c < n_rows */
 
 int b200_pack_cat(const b200_packcat_entry* table_dev, int32_t count, int32_t max_elems,
                   b200_stream_t stream);

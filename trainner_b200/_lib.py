@@ -78,7 +78,24 @@ class PackCatEntry(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p),
                 ("cout", C.c_int32), ("cin", C.c_int32), ("taps", C.c_int32), ("ci_off", C.c_int32),
                 ("n_rows", C.c_int32), ("rows_pad", C.c_int32), ("cols_pad", C.c_int32), ("col_off", C.c_int32),
-                ("scale", C.c_float), ("pad_", C.c_int32)]
+                ("scale", C.c_float), ("row_off", C.c_int32), ("mode", C.c_int32), ("pad_", C.c_int32)]
+
+
+class RdbStage(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("cx", C.c_int32), ("cin_off", C.c_int32), ("cin", C.c_int32),
+                ("w_packed", C.c_void_p),
+                ("out", C.c_void_p), ("out_c", C.c_int32), ("out_coff", C.c_int32),
+                ("bias", C.c_void_p),
+                ("mask", C.c_void_p), ("mask_c", C.c_int32), ("mask_coff", C.c_int32),
+                ("res1", C.c_void_p), ("res1_c", C.c_int32), ("res1_coff", C.c_int32),
+                ("res2", C.c_void_p), ("res2_c", C.c_int32), ("res2_coff", C.c_int32),
+                ("alpha", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("slope", C.c_float),
+                ("mask_slope", C.c_float), ("act", C.c_int32)]
+
+
+class RdbDesc(C.Structure):
+    _fields_ = [("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("flip_taps", C.c_int32),
+                ("stage", RdbStage * 5)]
 
 
 class PackEntry(C.Structure):
@@ -96,6 +113,7 @@ _SIGNATURES = {
     "b200_conv_igemm": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P],
     "b200_conv3x3_flat": [C.POINTER(FlatDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "b200_pack_cat": [_P, _I, _I, _P],
+    "b200_rdb_persist": [C.POINTER(RdbDesc), _P, _I, _P],
     "b200_pad_copy": [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_unpad_add": [_P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P],
     "b200_conv_wgrad": [C.POINTER(WgradDesc), _P, _P, _P, _P, _P],

@@ -236,10 +236,12 @@ __global__ void pack_cat_kernel(const b200_packcat_entry* __restrict__ table) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int co = (int)(i % e.cout);
-    const int r = (int)((i / e.cout) % e.n_rows);
+    const int r = (int)((i / e.cout) % e.n_rows);     // input-channel index within the block
     const int t = (int)(i / ((long long)e.cout * e.n_rows));
     const float v = e.scale * e.src[((size_t)co * e.cin + e.ci_off + r) * e.taps + t];
-    dst[((size_t)t * e.rows_pad + r) * e.cols_pad + e.col_off + co] = __float2bfloat16(v);
+    const size_t row = e.mode ? (size_t)(e.row_off + r) : (size_t)(e.row_off + co);
+    const size_t col = e.mode ? (size_t)(e.col_off + co) : (size_t)(e.col_off + r);
+    dst[((size_t)t * e.rows_pad + row) * e.cols_pad + col] = __float2bfloat16(v);
   }
 }
 

@@ -199,33 +199,15 @@ thin_wgrad_kernel(const float* __restrict__ thin, const __nv_bfloat16* __restric
     __syncthreads();
     if (j < cw) {
       const __nv_bfloat16* wrow = wide + ((size_t)b * h + yy) * w * cwide_buf + wide_coff + j;
-      // 4 consecutive pixels per iteration: 3x6 thin values per channel feed 4 x 9 FMAs
-      for (int x0 = sub * 4; x0 < w; x0 += 16) {
-        float v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          v[q] = (x0 + q < w) ? __bfloat162float(wrow[(size_t)(x0 + q) * cwide_buf]) : 0.f;
-          bsum += v[q];
-        }
+      for (int xx = sub; xx < w; xx += 4) {
+        const float v = __bfloat162float(wrow[(size_t)xx * cwide_buf]);
+        bsum += v;
 #pragma unroll
         for (int ci = 0; ci < CS; ++ci)
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-            const int r = 1 + sign * (ky - 1);
-            // columns x0-1 .. x0+4 of the patch row (index +1 for the left halo); zero beyond the row
-            float tv[6];
-#pragma unroll
-            for (int q = 0; q < 6; ++q) {
-              const int px = x0 + q;  // == (x0 - 1 + q) + 1
-              tv[q] = (px < wp) ? rows[(ci * 3 + r) * wp + px] : 0.f;
-            }
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const int dx = sign * (kx - 1);
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                acc[ci * 9 + ky * 3 + kx] = fmaf(v[q], tv[q + 1 + dx], acc[ci * 9 + ky * 3 + kx]);
-            }
+          for (int t = 0; t < 9; ++t) {
+            const int dy = sign * (t / 3 - 1), dx = sign * (t % 3 - 1);
+            acc[ci * 9 + t] = fmaf(v, rows[(ci * 3 + 1 + dy) * wp + xx + 1 + dx], acc[ci * 9 + t]);
           }
       }
     }

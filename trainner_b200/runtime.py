@@ -7,6 +7,7 @@ Running a plan is a tight loop of ctypes calls on the current CUDA stream (no te
 dispatcher), so the host stays far ahead of the GPU and the whole step is CUDA-graph capturable.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -29,6 +30,10 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+def sm_count_hint():
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
+
 def roundup(v, m):
     return (v + m - 1) // m * m
 
@@ -37,11 +42,14 @@ class Plan:
     """A list of (C function, argument tuple); the stream is appended at run time."""
 
     detail_sink = None  # set to a list to collect (tag, info, ms, flops) per call from run_timed()
+    use_graphs = os.environ.get("B200_GRAPHS", "1") != "0"
 
     def __init__(self):
         self.calls = []
         self.meta = []   # (kernel tag, algorithmic FLOPs) per call, for the roofline report
         self._keep = []
+        self._graph = None
+        self._runs = 0
 
     def add(self, fn, *args, flops=0.0, tag=None, info=""):
         self.calls.append((fn, args))
@@ -51,12 +59,34 @@ class Plan:
         self._keep.append(obj)
         return obj
 
-    def run(self):
+    def _run_eager(self):
         s = stream_ptr()
         for fn, args in self.calls:
             if fn(*args, s):
                 raise RuntimeError("trainner_b200 kernel call %s failed: %s" %
                                    (fn.__name__, lib.b200_last_error().decode()))
+
+    def run(self):
+        """Eager for the first two runs (lazy one-time initialisation inside the library), then the
+        plan is captured once into a CUDA graph and replayed: every pointer in a plan is static, so
+        the graph stays valid for the life of the context.  B200_GRAPHS=0 disables capture."""
+        if not Plan.use_graphs or self._graph is False or len(self.calls) < 8:
+            return self._run_eager()
+        if self._graph is None:
+            self._runs += 1
+            if self._runs <= 2:
+                return self._run_eager()
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run_eager()
+                self._graph = g
+            except Exception:
+                self._graph = False   # not capturable on this setup: stay eager
+                torch.cuda.synchronize()
+                return self._run_eager()
+        self._graph.replay()
 
     def run_timed(self):
         """Run with a CUDA event pair around every call (on the launching stream); returns
