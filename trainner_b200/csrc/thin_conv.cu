@@ -199,16 +199,38 @@ thin_wgrad_kernel(const float* __restrict__ thin, const __nv_bfloat16* __restric
     __syncthreads();
     if (j < cw) {
       const __nv_bfloat16* wrow = wide + ((size_t)b * h + yy) * w * cwide_buf + wide_coff + j;
-      for (int xx = sub; xx < w; xx += 4) {
-        const float v = __bfloat162float(wrow[(size_t)xx * cwide_buf]);
-        bsum += v;
+      // each pixel subset walks a contiguous quarter of the row with a 3-wide sliding window of the thin
+      // values per (channel, kernel row): 9 shared-memory loads (warp broadcast) feed 27 FMAs per pixel
+      const int seg = (w + 3) / 4;
+      const int xa = sub * seg, xb = min(xa + seg, w);
+      if (xa < xb) {
+        float win[CS * 3][3];
 #pragma unroll
-        for (int ci = 0; ci < CS; ++ci)
+        for (int q = 0; q < CS * 3; ++q) {
+          const int ci = q / 3, ky = q % 3;
+          const int r = 1 + sign * (ky - 1);
+          const float* rp = rows + (ci * 3 + r) * wp;
+          win[q][0] = (xa >= 1) ? rp[xa - 1 + 1] : rp[0];   // column xa-1 (index +1 for the left halo)
+          win[q][1] = rp[xa + 1];
+          win[q][2] = 0.f;
+        }
+        for (int xx = xa; xx < xb; ++xx) {
+          const float v = __bfloat162float(wrow[(size_t)xx * cwide_buf]);
+          bsum += v;
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const int dy = sign * (t / 3 - 1), dx = sign * (t % 3 - 1);
-            acc[ci * 9 + t] = fmaf(v, rows[(ci * 3 + 1 + dy) * wp + xx + 1 + dx], acc[ci * 9 + t]);
+          for (int q = 0; q < CS * 3; ++q) {
+            const int ci = q / 3, ky = q % 3;
+            const int r = 1 + sign * (ky - 1);
+            win[q][2] = rows[(ci * 3 + r) * wp + xx + 2];   // column xx+1
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const float tv = (sign > 0) ? win[q][kx] : win[q][2 - kx];   // column xx + sign*(kx-1)
+              acc[ci * 9 + ky * 3 + kx] = fmaf(v, tv, acc[ci * 9 + ky * 3 + kx]);
+            }
+            win[q][0] = win[q][1];
+            win[q][1] = win[q][2];
           }
+        }
       }
     }
   }
