@@ -217,6 +217,112 @@ probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pipeline emulation (mode "pipe"): the conv_flat issue structure without any TMA traffic.
+// warps 0..nissue-1 issue G MMAs per stage (own accumulator), commit the stage's "empty" barrier
+// and move on; warp 3 is the producer: waits "empty", arrives "full".  Measures what the
+// barrier handshakes and commits cost on top of the raw MMA rate (mode 3).
+struct PipeParams {
+  int N, G, S, groups, nissue;
+  int commit_only;   // 1: no full/empty handshake, just a commit every G MMAs
+  int sep;           // bit 0: issuers read different A tiles, bit 1: different B tiles
+  int dstride;       // TMEM column distance between the issuers' accumulators
+  int data;          // 0: all-zero operands, 1: random bf16 operands
+};
+
+__global__ void __launch_bounds__(352, 1)
+pipe_kernel(PipeParams p, long long* __restrict__ cycles, int* __restrict__ err) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full[8], empty[8], done[4];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], p.nissue);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&done[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  const uint32_t a_stage = 144 * 128, b_stage = 256 * 128;
+  for (uint32_t i = threadIdx.x; i < (4 * (a_stage + b_stage)) / 4; i += blockDim.x) {
+    uint32_t r = (i + 1) * 2654435761u;
+    r ^= r >> 13;
+    // two bf16 in (0.0078 .. 2), random sign: realistic switching activity instead of all-zero operands
+    uint32_t v = (0x3C003C00u | (r & 0x03FF03FFu) | ((r << 3) & 0x80008000u));
+    reinterpret_cast<uint32_t*>(smem)[i] = p.data ? v : 0u;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  bool ok = true;
+  if (warp < p.nissue) {
+    const uint32_t idesc = make_idesc_bf16(128, p.N, 0, 0);
+    const uint32_t a0 = smem_u32(smem), b0 = a0 + 4 * a_stage;
+    const uint64_t desc_hi = make_smem_desc(0, 16, 1024, LAYOUT_SW128, 0);
+    int st = 0;
+    uint32_t ph = 0;
+    long long t0 = clock64();
+    for (int g = 0; g < p.groups; ++g) {
+      if (!p.commit_only) {
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+      }
+      const uint32_t a_addr = a0 + ((g + ((p.sep & 1) ? 2 * warp : 0)) & 3) * a_stage + (g % 7) * 128;
+      const uint32_t b_addr = b0 + ((g + ((p.sep & 2) ? 2 * warp : 0)) & 3) * b_stage;
+      if (elect_one()) {
+        for (int j = 0; j < p.G; j += 4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint64_t ad = desc_hi | (uint64_t)(((a_addr + k * 32) >> 4) & 0x3FFF);
+            uint64_t bd = desc_hi | (uint64_t)(((b_addr + ((j >> 2) & 3) * 8192 + k * 32) >> 4) & 0x3FFF);
+            umma_f16(tmem + warp * p.dstride, ad, bd, idesc, (g | j | k) != 0);
+          }
+        }
+        umma_commit(&empty[st]);
+      }
+      __syncwarp();
+      if (++st == p.S) {
+        st = 0;
+        ph ^= 1;
+      }
+    }
+    if (elect_one()) umma_commit(&done[warp]);
+    __syncwarp();
+    ok = wait_bounded(&done[warp], 0);
+    long long t1 = clock64();
+    if (lane_id() == 0) {
+      atomicMax((unsigned long long*)&cycles[blockIdx.x], (unsigned long long)(t1 - t0));
+      if (!ok) *err = 1;
+    }
+  } else if (warp >= 4) {
+    // spinners: emulate epilogue warps polling an mbarrier that completes only when issuer 0 is done
+    mbar_wait(&done[0], 0);
+  } else if (warp == 3 && !p.commit_only) {
+    int st = 0;
+    uint32_t ph = 0;
+    for (int g = 0; g < p.groups; ++g) {
+      mbar_wait(&empty[st], ph ^ 1);
+      if (elect_one()) mbar_arrive(&full[st]);
+      __syncwarp();
+      if (++st == p.S) {
+        st = 0;
+        ph ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 struct Case {
@@ -264,7 +370,7 @@ int main(int argc, char** argv) {
   cases.push_back({"mnmajor_B_sw64", {2, 32, 128, 0, 0, 128, 0, 0}});
   cases.push_back({"mnmajor_B_sw64_shift", {2, 32, 128, 5, 0, 136, 0, 0}});
 
-  if (argc > 1 && !strcmp(argv[1], "rate")) cases.clear();
+  if (argc > 1 && (!strcmp(argv[1], "rate") || !strcmp(argv[1], "pipe"))) cases.clear();
   for (auto& cs : cases) {
     Params p = cs.p;
     // host data
@@ -353,13 +459,48 @@ int main(int argc, char** argv) {
     cudaFree(dB);
   }
 
+  if (argc > 1 && !strcmp(argv[1], "pipe")) {
+    CK(cudaFuncSetAttribute(pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    for (int threads : {352})
+    for (int data : {0, 1})
+    for (int dstride : {128})
+    for (int sep : {3})
+    for (int commit_only : {1, 0})
+      for (int N : {32, 64})
+        for (int G : {4, 12, 36})
+          for (int S : {2, 3, 4, 8}) {
+            if (S != 3 || G == 4 || commit_only) continue;
+            if (dstride < N) continue;
+            PipeParams pp = {N, G, S, 1440 / G, 2, commit_only, sep, dstride, data};
+            for (int it = 0; it < 2; ++it) {
+              CK(cudaMemset(derr, 0, sizeof(int)));
+              CK(cudaMemset(dcyc, 0, 1024 * sizeof(long long)));
+              pipe_kernel<<<148, threads, SMEM>>>(pp, dcyc, derr);
+              CK(cudaDeviceSynchronize());
+            }
+            std::vector<long long> cyc(148);
+            CK(cudaMemcpy(cyc.data(), dcyc, 148 * sizeof(long long), cudaMemcpyDeviceToHost));
+            long long mx = 0;
+            for (auto c : cyc) mx = c > mx ? c : mx;
+            int herr = 0;
+            CK(cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost));
+            printf("pipe data=%d dstride=%d threads=%d %s sep=%d N=%2d G=%2d stages=%d : %.1f cyc/MMA aggregate (2 issuers)%s\n",
+                   data, dstride, threads, commit_only ? "commit-only" : "full/empty ", sep, N, G, S, (double)mx / (1440.0 * 2), herr ? " TIMEOUT" : "");
+          }
+    printf("done\n");
+    return 0;
+  }
   // ---- rate ----
   {
     CUtensorMap dummy;
     memset(&dummy, 0, sizeof(dummy));
+    const bool shift_sweep = argc > 2 && !strcmp(argv[2], "shift");
+    for (int shift : {0, 1, 2, 3, 5, 7})
     for (int nissue : {1, 2, 4})
       for (int N : {16, 32, 64, 128}) {
-          Params p = {3, N, 0, 0, 0, nissue, 4096, 0};
+          if (!shift_sweep && shift) continue;
+          if (shift_sweep && (nissue != 2 || N == 16)) continue;
+          Params p = {3, N, 0, shift, 0, nissue, 4096, 0};
           CK(cudaMemset(derr, 0, sizeof(int)));
           CK(cudaMemset(dcyc, 0, 1024 * sizeof(long long)));
           probe_kernel<<<148, 128, SMEM>>>(dummy, dummy, p, dD, dcyc, derr);
@@ -372,7 +513,7 @@ int main(int argc, char** argv) {
           long long mx = 0;
           for (auto c : cyc) mx = c > mx ? c : mx;
           double per = (double)mx / (p.reps * nissue);
-          printf("rate issuers=%d N=%3d : %.1f cyc/MMA aggregate (ideal %.1f)\n", nissue, N, per, N / 2.0);
+          printf("rate issuers=%d N=%3d A-shift=%d rows : %.1f cyc/MMA aggregate (ideal %.1f)\n", nissue, N, shift, per, N / 2.0);
       }
   }
   printf("done\n");

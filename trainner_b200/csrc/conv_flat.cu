@@ -61,6 +61,7 @@ struct FlatParams {
   int mask_c, mask_coff, mask_lo, mask_hi;
   float mask_slope;
   long long* dbg;  // optional per-CTA timeline (clock64), 16 slots per CTA; nullptr in production
+  int dbg_flags;   // experiments only (wrong results): 1 = skip weight reloads, 2 = skip activation reloads
 };
 
 #define DBG_T(slot) do { if (p.dbg && lane == 0) p.dbg[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
@@ -169,6 +170,53 @@ __device__ __forceinline__ void flat_epilogue(const FlatParams& p, const uint32_
   }
 }
 
+// One 64-channel K chunk of one 128-row half: 9 taps in groups of TPB taps per weight stage.  A single
+// elected lane issues a whole group inside ONE elect region: tcgen05.mma issue is nearly synchronous (the
+// queue is a few instructions deep), so every elect/reconverge boundary between MMAs is a bubble on the
+// tensor pipe whenever both issuers reach it together (tools/umma_probe.cu "pipe": a boundary every
+// 4 MMAs costs 57 cycles/MMA, every 12 or 36 MMAs the hardware's 40.7 / 48.5).
+template <int TPB>
+__device__ __forceinline__ void flat_issue_chunk(const FlatParams& p, const uint32_t (&sh16)[9], uint32_t a16,
+                                                 int nk, bool first_c, bool last_c,
+                                                 uint32_t d_tmem, uint32_t idesc, uint64_t desc_hi,
+                                                 uint32_t b_ring16, uint32_t b_stage16, uint32_t btap16,
+                                                 int& bs, uint32_t& bph, uint64_t* b_full, uint64_t* b_empty,
+                                                 uint64_t* a_empty_bar, uint64_t* tfull) {
+#pragma unroll
+  for (int g = 0; g < 9 / TPB; ++g) {
+    mbar_wait(&b_full[bs], bph);
+    tc_fence_after();
+    const uint32_t b16 = b_ring16 + bs * b_stage16;
+    if (elect_one()) {
+#pragma unroll
+      for (int j = 0; j < TPB; ++j) {
+        const int t = g * TPB + j;
+        const uint32_t at = a16 + sh16[t], bt = b16 + j * btap16;
+        if (nk == 4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(d_tmem, desc_hi | (uint64_t)(at + 2 * k), desc_hi | (uint64_t)(bt + 2 * k), idesc,
+                     !(first_c && t == 0 && k == 0));
+        } else {
+          for (int k = 0; k < nk; ++k)
+            umma_f16(d_tmem, desc_hi | (uint64_t)(at + 2 * k), desc_hi | (uint64_t)(bt + 2 * k), idesc,
+                     !(first_c && t == 0 && k == 0));
+        }
+      }
+      umma_commit(&b_empty[bs]);
+      if (g == 9 / TPB - 1) {
+        umma_commit(a_empty_bar);
+        if (last_c) umma_commit(tfull);
+      }
+    }
+    __syncwarp();
+    if (++bs == p.b_stages) {
+      bs = 0;
+      bph ^= 1;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_flat_kernel(const __grid_constant__ FlatParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -178,7 +226,7 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
       b_empty[kMaxBStages], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   if (warp == 0) DBG_T(0);
   if (threadIdx.x == 0) {
@@ -219,7 +267,9 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
       const int row0 = tile * kTileM - p.halo;
       for (int c = 0; c < p.k_chunks; ++c) {
         mbar_wait(&a_empty[as], aph ^ 1);
-        if (elect_one()) {
+        if ((p.dbg_flags & 2) && (tile != (int)blockIdx.x || c >= p.a_stages)) {
+          if (elect_one()) mbar_arrive(&a_full[as]);
+        } else if (elect_one()) {
           uint8_t* sa = smem + (size_t)as * p.a_stage_bytes;
           mbar_expect_tx(&a_full[as], p.a_bytes);
           const CUtensorMap* im = (c < p.kc1) ? &p.in_map : &p.in2_map;
@@ -234,7 +284,9 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
         }
         for (int t0 = 0; t0 < 9; t0 += p.tpb) {
           mbar_wait(&b_empty[bs], bph ^ 1);
-          if (elect_one()) {
+          if ((p.dbg_flags & 1) && (tile != (int)blockIdx.x || c > 0)) {
+            if (elect_one()) mbar_arrive(&b_full[bs]);
+          } else if (elect_one()) {
             uint8_t* sb = smem + p.b_ring_off + (size_t)bs * p.b_stage_bytes;
             mbar_expect_tx(&b_full[bs], p.b_bytes * p.tpb);
             for (int j = 0; j < p.tpb; ++j)
@@ -257,6 +309,16 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
     const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
     const uint64_t desc_hi = make_smem_desc(0, 16, 1024, LAYOUT_SW128, 0);
     const uint32_t smem_base = smem_u32(smem);
+    // Everything the issue loop touches is warp-uniform (the warp index comes from a shuffle so that the
+    // compiler can prove it) and the nine tap offsets live in registers: the descriptor of an MMA is then
+    // two uniform adds away from the previous one.  With per-tap constant-bank loads and R2UR moves in
+    // the loop the issuers managed only one MMA per ~130 cycles each (tools/umma_probe.cu "pipe" reaches
+    // the hardware's 40/48 cycles per MMA with the same barrier structure).
+    uint32_t sh16[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) sh16[t] = (uint32_t)(p.tap_shift[t] * 8);   // rows of 128 B, in 16-B units
+    const uint32_t btap16 = p.b_tap_bytes >> 4;
+    const uint32_t b_ring16 = (smem_base + p.b_ring_off) >> 4, b_stage16 = p.b_stage_bytes >> 4;
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
     int acc = 0;
@@ -270,33 +332,17 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
         tc_fence_after();
         if (half == 0 && tile == (int)blockIdx.x && c == 0) DBG_T(2);
         const int nk = (c == p.k_chunks - 1) ? p.last_k16 : ((c == p.kc1 - 1) ? p.last1_k16 : 4);
-        const uint32_t a_base = smem_base + as * p.a_stage_bytes + (uint32_t)(p.halo + half * 128) * 128;
-        for (int t0 = 0; t0 < 9; t0 += p.tpb) {
-          mbar_wait(&b_full[bs], bph);
-          tc_fence_after();
-          const uint32_t b_base = smem_base + p.b_ring_off + bs * p.b_stage_bytes;
-          if (elect_one()) {
-            for (int j = 0; j < p.tpb; ++j) {
-              const uint32_t a_addr = a_base + (uint32_t)(p.tap_shift[t0 + j] * 128);
-              const uint32_t b_addr = b_base + j * p.b_tap_bytes;
-              for (int k = 0; k < nk; ++k) {
-                const uint64_t bd = desc_hi | (uint64_t)(((b_addr + k * 32) >> 4) & 0x3FFF);
-                const uint64_t ad = desc_hi | (uint64_t)(((a_addr + k * 32) >> 4) & 0x3FFF);
-                umma_f16(d_tmem, ad, bd, idesc, (c | (t0 + j) | k) != 0);
-              }
-            }
-            umma_commit(&b_empty[bs]);
-            if (t0 + p.tpb >= 9) {
-              umma_commit(&a_empty[as]);
-              if (c == p.k_chunks - 1) umma_commit(&tfull_bar[acc]);
-            }
-          }
-          __syncwarp();
-          if (++bs == p.b_stages) {
-            bs = 0;
-            bph ^= 1;
-          }
-        }
+        const uint32_t a16 = (smem_base + as * p.a_stage_bytes + (uint32_t)(p.halo + half * 128) * 128) >> 4;
+        const bool first_c = (c == 0), last_c = (c == p.k_chunks - 1);
+        if (p.tpb == 9)
+          flat_issue_chunk<9>(p, sh16, a16, nk, first_c, last_c, d_tmem, idesc, desc_hi, b_ring16, b_stage16,
+                              btap16, bs, bph, b_full, b_empty, &a_empty[as], &tfull_bar[acc]);
+        else if (p.tpb == 3)
+          flat_issue_chunk<3>(p, sh16, a16, nk, first_c, last_c, d_tmem, idesc, desc_hi, b_ring16, b_stage16,
+                              btap16, bs, bph, b_full, b_empty, &a_empty[as], &tfull_bar[acc]);
+        else
+          flat_issue_chunk<1>(p, sh16, a16, nk, first_c, last_c, d_tmem, idesc, desc_hi, b_ring16, b_stage16,
+                              btap16, bs, bph, b_full, b_empty, &a_empty[as], &tfull_bar[acc]);
         if (++as == p.a_stages) {
           as = 0;
           aph ^= 1;
@@ -317,6 +363,7 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      if (p.dbg_flags & 4) break;
       const long long m = (long long)tile * kTileM + half * 128 + quad * 32 + lane;
       const int nimg = (int)(m / p.HpWp);
       const int rem = (int)(m - (long long)nimg * p.HpWp);
@@ -538,6 +585,8 @@ extern "C" int b200_conv3x3_flat(const b200_flat_desc* d, const void* x, const v
   {
     const char* e = getenv("B200_FLAT_DBG_PTR");
     p.dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+    const char* f = getenv("B200_FLAT_DBG_FLAGS");
+    p.dbg_flags = f ? atoi(f) : 0;
   }
   const int sms = sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
