@@ -144,13 +144,15 @@ def test_thin_convs():
     wg = w.clone().requires_grad_(True)
     bg = b.clone().requires_grad_(True)
     F.conv2d(x, wg, bg, padding=1).backward(dy)
+    # the thin operand (an fp32 image) is rounded to bf16 for the tensor-core kernels, as the reference's
+    # autocast path rounds every conv input: rms rounding error 2^-9/sqrt(3) = 1.1e-3 per element
     dw, dbw, _ = ops.conv3x3_thin_wgrad(x, nhwc(dy), True, want_bias_wide=True)
-    assert rel(dw, wg.grad) < 1e-3 and rel(dbw, bg.grad) < 1e-3
+    assert rel(dw, wg.grad) < 3e-3 and rel(dbw, bg.grad) < 1e-3
     w2g = w2.clone().requires_grad_(True)
     b2g = b2.clone().requires_grad_(True)
     F.conv2d(xw, w2g, b2g, padding=1).backward(dyt)
     dw2, _, dbt = ops.conv3x3_thin_wgrad(dyt, nhwc(xw), False, want_bias_thin=True)
-    assert rel(dw2, w2g.grad) < 1e-3 and rel(dbt, b2g.grad) < 1e-3
+    assert rel(dw2, w2g.grad) < 3e-3 and rel(dbt, b2g.grad) < 1e-3
 
 
 @pytest.mark.parametrize("N,H,W,C", [(4, 16, 16, 64), (2, 8, 8, 512), (16, 32, 32, 128)])

@@ -209,39 +209,44 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __res
   }
 }
 
+// One thread converts all taps of one (row, col) weight: the fp32 source is read as `taps` consecutive
+// floats (coalesced across the warp along the source's fastest dimension) instead of one strided gather
+// per tap, and every tap plane of the destination is written with consecutive columns.
 __global__ void pack_weights_kernel(const b200_pack_entry* __restrict__ table, int count) {
   const b200_pack_entry e = table[blockIdx.y];
-  const long long total = (long long)e.taps * e.rows_pad * e.cols_pad;
+  const long long total = (long long)e.rows_pad * e.cols_pad;
+  const long long plane = total;
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.dst);
+  const int mul = e.co_mul ? e.co_mul : 1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % e.cols_pad);
-    const int r = (int)((i / e.cols_pad) % e.rows_pad);
-    const int t = (int)(i / ((long long)e.cols_pad * e.rows_pad));
-    float v = 0.f;
-    const int mul = e.co_mul ? e.co_mul : 1;
+    const int r = (int)(i / e.cols_pad);
+    const float* src = nullptr;
     if (e.mode == 0) {  // rows = co, cols = ci
-      if (r < e.cout && c < e.cin) v = e.src[((size_t)(r * mul + e.co_off) * e.cin + c) * e.taps + t];
+      if (r < e.cout && c < e.cin) src = e.src + ((size_t)(r * mul + e.co_off) * e.cin + c) * e.taps;
     } else {            // rows = ci, cols = co
-      if (r < e.cin && c < e.cout) v = e.src[((size_t)(c * mul + e.co_off) * e.cin + r) * e.taps + t];
+      if (r < e.cin && c < e.cout) src = e.src + ((size_t)(c * mul + e.co_off) * e.cin + r) * e.taps;
     }
-    dst[i] = __float2bfloat16(v);
+    for (int t = 0; t < e.taps; ++t) dst[t * plane + i] = __float2bfloat16(src ? src[t] : 0.f);
   }
 }
 
 __global__ void pack_cat_kernel(const b200_packcat_entry* __restrict__ table) {
   const b200_packcat_entry e = table[blockIdx.y];
-  const long long total = (long long)e.taps * e.n_rows * e.cout;
+  const long long total = (long long)e.n_rows * e.cout;
+  const size_t plane = (size_t)e.rows_pad * e.cols_pad;
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.dst);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int co = (int)(i % e.cout);
-    const int r = (int)((i / e.cout) % e.n_rows);     // input-channel index within the block
-    const int t = (int)(i / ((long long)e.cout * e.n_rows));
-    const float v = e.scale * e.src[((size_t)co * e.cin + e.ci_off + r) * e.taps + t];
+    // the destination's fastest dimension is the fastest thread dimension
+    const int r = e.mode ? (int)(i / e.cout) : (int)(i % e.n_rows);    // input-channel index within the block
+    const int co = e.mode ? (int)(i % e.cout) : (int)(i / e.n_rows);
+    const float* src = e.src + ((size_t)co * e.cin + e.ci_off + r) * e.taps;
     const size_t row = e.mode ? (size_t)(e.row_off + r) : (size_t)(e.row_off + co);
     const size_t col = e.mode ? (size_t)(e.col_off + co) : (size_t)(e.col_off + r);
-    dst[((size_t)t * e.rows_pad + row) * e.cols_pad + col] = __float2bfloat16(v);
+    for (int t = 0; t < e.taps; ++t)
+      dst[(size_t)t * plane + row * e.cols_pad + col] = __float2bfloat16(e.scale * src[t]);
   }
 }
 

@@ -64,39 +64,57 @@ __global__ void bn_reduce_kernel(const __nv_bfloat16* __restrict__ z,
       be[j] = beta[cv + j];
     }
   }
-  for (; i < total_vec; i += stride) {
-    float f[8];
-    unpack8(reinterpret_cast<const uint4*>(z)[i], f);
-    if (MODE == 0) {
+  constexpr int U = 4;
+  for (; i < total_vec; i += U * stride) {
+    uint4 zv[U], gv[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s0[j] += f[j];
-        s1[j] = fmaf(f[j], f[j], s1[j]);
-      }
-    } else {
-      float g[8];
-      unpack8(reinterpret_cast<const uint4*>(da)[i], g);
+    for (int u = 0; u < U; ++u) {
+      const long long iu = i + u * stride;
+      zv[u] = iu < total_vec ? reinterpret_cast<const uint4*>(z)[iu] : make_uint4(0, 0, 0, 0);
+      if (MODE == 1) gv[u] = iu < total_vec ? reinterpret_cast<const uint4*>(da)[iu] : make_uint4(0, 0, 0, 0);
+    }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float zh = (f[j] - mu[j]) * is[j];
-        const float bn = fmaf(ga[j], zh, be[j]);
-        const float d = bn > 0.f ? g[j] : g[j] * slope;
-        s0[j] += d;
-        s1[j] = fmaf(d, zh, s1[j]);
+    for (int u = 0; u < U; ++u) {
+      if (i + u * stride >= total_vec) break;
+      float f[8];
+      unpack8(zv[u], f);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s0[j] += f[j];
+          s1[j] = fmaf(f[j], f[j], s1[j]);
+        }
+      } else {
+        float g[8];
+        unpack8(gv[u], g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float zh = (f[j] - mu[j]) * is[j];
+          const float bn = fmaf(ga[j], zh, be[j]);
+          const float d = bn > 0.f ? g[j] : g[j] * slope;
+          s0[j] += d;
+          s1[j] = fmaf(d, zh, s1[j]);
+        }
       }
     }
   }
-  // block reduction per channel lane through shared memory atomics
-  extern __shared__ float sh[];  // [2][c]
-  for (int k = threadIdx.x; k < 2 * c; k += blockDim.x) sh[k] = 0.f;
-  __syncthreads();
+  // block reduction without shared-memory float atomics (a CAS loop under 32-way same-address
+  // contention was most of this kernel's time): every thread parks its 16 partial sums, then one
+  // thread per output adds the 256 / vec_per_pix threads that share its channel lane.
+  extern __shared__ float sh[];  // [16][256]
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sh[cv + j], s0[j]);
-    atomicAdd(&sh[c + cv + j], s1[j]);
+    sh[j * 256 + threadIdx.x] = s0[j];
+    sh[(8 + j) * 256 + threadIdx.x] = s1[j];
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < 2 * c; k += blockDim.x) atomicAdd(&sums[k], sh[k]);
+  for (int k = threadIdx.x; k < 2 * c; k += blockDim.x) {
+    const int which = k / c, ch = k - which * c;
+    const int ln = ch >> 3, j = (ch & 7) + 8 * which;
+    float t = 0.f;
+    for (int q = ln; q < 256; q += vec_per_pix) t += sh[j * 256 + q];
+    atomicAdd(&sums[k], t);
+  }
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, float* __restrict__ mean_invstd,
@@ -142,27 +160,40 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z,
       m1[j] = sums[c + cv + j] * inv_n;
     }
   }
-  for (; i < total_vec; i += stride) {
-    float f[8], o[8];
-    unpack8(reinterpret_cast<const uint4*>(z)[i], f);
-    if (MODE == 0) {
+  constexpr int U = 2;
+  for (; i < total_vec; i += U * stride) {
+    uint4 zv[U], gv[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float bn = fmaf(ga[j], (f[j] - mu[j]) * is[j], be[j]);
-        o[j] = bn > 0.f ? bn : bn * slope;
-      }
-    } else {
-      float g[8];
-      unpack8(reinterpret_cast<const uint4*>(da)[i], g);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float zh = (f[j] - mu[j]) * is[j];
-        const float bn = fmaf(ga[j], zh, be[j]);
-        const float d = bn > 0.f ? g[j] : g[j] * slope;
-        o[j] = ga[j] * is[j] * (d - m0[j] - zh * m1[j]);
-      }
+    for (int u = 0; u < U; ++u) {
+      const long long iu = i + u * stride;
+      zv[u] = iu < total_vec ? reinterpret_cast<const uint4*>(z)[iu] : make_uint4(0, 0, 0, 0);
+      if (MODE == 1) gv[u] = iu < total_vec ? reinterpret_cast<const uint4*>(da)[iu] : make_uint4(0, 0, 0, 0);
     }
-    reinterpret_cast<uint4*>(out)[i] = pack8(o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long iu = i + u * stride;
+      if (iu >= total_vec) break;
+      float f[8], o[8];
+      unpack8(zv[u], f);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float bn = fmaf(ga[j], (f[j] - mu[j]) * is[j], be[j]);
+          o[j] = bn > 0.f ? bn : bn * slope;
+        }
+      } else {
+        float g[8];
+        unpack8(gv[u], g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float zh = (f[j] - mu[j]) * is[j];
+          const float bn = fmaf(ga[j], zh, be[j]);
+          const float d = bn > 0.f ? g[j] : g[j] * slope;
+          o[j] = ga[j] * is[j] * (d - m0[j] - zh * m1[j]);
+        }
+      }
+      reinterpret_cast<uint4*>(out)[iu] = pack8(o);
+    }
   }
 }
 
@@ -378,9 +409,9 @@ __global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict_
 }
 
 // grid such that (grid*256) % vec_per_pix == 0 so each thread keeps one channel lane
-inline int bn_grid(long long npix, int c) {
+inline int bn_grid(long long npix, int c, int per_thread) {
   const int vpp = c / 8;
-  long long total = npix * vpp;
+  long long total = (npix * vpp + per_thread - 1) / per_thread;
   int g = grid_for(total, 256, 148 * 8);
   // 256 * g divisible by vpp: vpp is a power of two <= 64 for c in {64,128,256,512}; otherwise fix up
   while ((256LL * g) % vpp != 0) ++g;
@@ -396,9 +427,9 @@ typedef __nv_bfloat16 bf16;
 extern "C" {
 
 int b200_bn_stats(const void* z, float* stats, int64_t npix, int32_t c, b200_stream_t stream) {
-  B200_REQUIRE(c % 8 == 0 && c <= 2048, "b200_bn_stats: c must be a multiple of 8");
+  B200_REQUIRE(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "b200_bn_stats: c/8 must be a power of two <= 256 (c=%d)", c);
   B200_CHECK_CUDA(cudaMemsetAsync(stats, 0, 2 * c * sizeof(float), as_stream(stream)));
-  bn_reduce_kernel<0><<<bn_grid(npix, c), 256, 2 * c * sizeof(float), as_stream(stream)>>>(
+  bn_reduce_kernel<0><<<bn_grid(npix, c, 4), 256, 16 * 256 * sizeof(float), as_stream(stream)>>>(
       (const bf16*)z, nullptr, nullptr, nullptr, nullptr, stats, npix, c, 0.f);
   B200_LAUNCH_CHECK();
   return 0;
@@ -417,7 +448,7 @@ int b200_bn_apply_lrelu(const void* z, const float* mean_invstd, const float* ga
                         const float* beta, void* a, int64_t npix, int32_t c, float slope,
                         b200_stream_t stream) {
   B200_REQUIRE(c % 8 == 0, "b200_bn_apply_lrelu: c must be a multiple of 8");
-  bn_apply_kernel<0><<<bn_grid(npix, c), 256, 0, as_stream(stream)>>>(
+  bn_apply_kernel<0><<<bn_grid(npix, c, 2), 256, 0, as_stream(stream)>>>(
       (const bf16*)z, nullptr, mean_invstd, gamma, beta, nullptr, (bf16*)a, npix, c, slope);
   B200_LAUNCH_CHECK();
   return 0;
@@ -426,9 +457,9 @@ int b200_bn_apply_lrelu(const void* z, const float* mean_invstd, const float* ga
 int b200_bn_bwd_reduce(const void* z, const void* da, const float* mean_invstd, const float* gamma,
                        const float* beta, float* sums, int64_t npix, int32_t c, float slope,
                        b200_stream_t stream) {
-  B200_REQUIRE(c % 8 == 0 && c <= 2048, "b200_bn_bwd_reduce: c must be a multiple of 8");
+  B200_REQUIRE(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "b200_bn_bwd_reduce: c/8 must be a power of two <= 256 (c=%d)", c);
   B200_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * c * sizeof(float), as_stream(stream)));
-  bn_reduce_kernel<1><<<bn_grid(npix, c), 256, 2 * c * sizeof(float), as_stream(stream)>>>(
+  bn_reduce_kernel<1><<<bn_grid(npix, c, 4), 256, 16 * 256 * sizeof(float), as_stream(stream)>>>(
       (const bf16*)z, (const bf16*)da, mean_invstd, gamma, beta, sums, npix, c, slope);
   B200_LAUNCH_CHECK();
   return 0;
@@ -437,7 +468,7 @@ int b200_bn_bwd_reduce(const void* z, const void* da, const float* mean_invstd, 
 int b200_bn_bwd_apply(const void* z, const void* da, const float* mean_invstd, const float* gamma,
                       const float* beta, const float* sums, void* dz, float* dgamma, float* dbeta,
                       int64_t npix, int32_t c, float slope, b200_stream_t stream) {
-  bn_apply_kernel<1><<<bn_grid(npix, c), 256, 0, as_stream(stream)>>>(
+  bn_apply_kernel<1><<<bn_grid(npix, c, 2), 256, 0, as_stream(stream)>>>(
       (const bf16*)z, (const bf16*)da, mean_invstd, gamma, beta, sums, (bf16*)dz, npix, c, slope);
   B200_LAUNCH_CHECK();
   if (dgamma) {

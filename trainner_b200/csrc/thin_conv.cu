@@ -253,6 +253,352 @@ thin_wgrad_kernel(const float* __restrict__ thin, const __nv_bfloat16* __restric
   }
 }
 
+// ================================================================= tensor-core (mma.sync) versions
+// The thin convolutions are HBM-bound layers with a degenerate GEMM shape (K = 27 or N = 3): the
+// CUDA-core kernels above are FMA/LDS-bound at 6-20x their memory roofline.  The kernels below do the
+// same arithmetic as warp-level m16n8k16 bf16 MMAs with fp32 accumulation (the thin operand is rounded
+// to bf16, which is what the reference's autocast path does to these conv inputs too); tcgen05 buys
+// nothing here because the tensor work is < 5 % of the memory time.
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---------------------------------------------------------------- thin -> wide, GEMM [px] x [27->16*KS] x [64]
+// block = 32 x 8 pixels, warp = one row of 32 pixels = two m16 tiles.  Output channel of (n-tile j, column c)
+// is 16*(c>>1) + 2*j + (c&1): the accumulator fragment of lane (g, t) is then 16 consecutive channels of
+// pixel rows g and g+8, stored as two 16-byte vectors each.
+template <int CS>
+__global__ void __launch_bounds__(256)
+thin_to_wide_mma_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
+                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int n, int h,
+                        int w, int cw, int cy, int y_coff, int transpose_w,
+                        const float* __restrict__ mean, const float* __restrict__ stdv, int act,
+                        float slope, const __nv_bfloat16* __restrict__ mask, int mask_c, int mask_coff,
+                        float mask_slope) {
+  constexpr int KS = (CS * 9 + 15) / 16;
+  extern __shared__ uint2 bfrag[];  // [cw/64][KS][8][32]
+  __shared__ float patch[CS * 10 * 34];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int groups = cw / 64;
+  for (int i = tid; i < groups * KS * 256; i += 256) {
+    const int l = i & 31, j = (i >> 5) & 7, ks = (i >> 8) % KS, grp = i / (256 * KS);
+    const int gg = l >> 2, tt = l & 3;
+    const int ch = grp * 64 + 16 * (gg >> 1) + 2 * j + (gg & 1);
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = 16 * ks + 2 * tt + (q & 1) + (q >> 1) * 8;
+      float r = 0.f;
+      if (k < CS * 9) {
+        const int ci = k / 9, tp = k % 9;
+        r = transpose_w ? wgt[((size_t)ci * cw + ch) * 9 + (8 - tp)] : wgt[((size_t)ch * CS + ci) * 9 + tp];
+      }
+      v[q] = r;
+    }
+    bfrag[i] = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
+  }
+  const int tiles_x = (w + 31) / 32, tiles_y = (h + 7) / 8;
+  const int b = blockIdx.x / (tiles_x * tiles_y);
+  const int tr = blockIdx.x % (tiles_x * tiles_y);
+  const int x0 = (tr % tiles_x) * 32, y0 = (tr / tiles_x) * 8;
+  for (int i = tid; i < CS * 10 * 34; i += 256) {
+    const int px = i % 34, py = (i / 34) % 10, ci = i / 340;
+    const int gx = x0 + px - 1, gy = y0 + py - 1;
+    float v = 0.f;
+    if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+      v = x[(((size_t)b * CS + ci) * h + gy) * w + gx];
+      if (mean) v = (v - mean[ci]) / stdv[ci];
+    }
+    patch[i] = v;
+  }
+  __syncthreads();
+  int off[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = 16 * ks + 2 * t + (q & 1) + (q >> 1) * 8;
+      off[ks][q] = k < CS * 9 ? (k / 9) * 340 + ((k % 9) / 3) * 34 + (k % 9) % 3 : -1;
+    }
+  const int gy = y0 + warp;
+#pragma unroll 1
+  for (int mt = 0; mt < 2; ++mt) {
+    const int xb = mt * 16;
+    const int base = warp * 34 + xb + g;
+    uint32_t a[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      float v[4][2];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[q][0] = off[ks][q] >= 0 ? patch[base + off[ks][q]] : 0.f;
+        v[q][1] = off[ks][q] >= 0 ? patch[base + 8 + off[ks][q]] : 0.f;
+      }
+      a[ks][0] = pack2(v[0][0], v[1][0]);
+      a[ks][1] = pack2(v[0][1], v[1][1]);
+      a[ks][2] = pack2(v[2][0], v[3][0]);
+      a[ks][3] = pack2(v[2][1], v[3][1]);
+    }
+    for (int grp = 0; grp < groups; ++grp) {
+      float acc[8][4];
+      const int cbase = grp * 64 + 16 * t;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float b0 = bias ? bias[cbase + 2 * j] : 0.f, b1 = bias ? bias[cbase + 2 * j + 1] : 0.f;
+        acc[j][0] = b0; acc[j][1] = b1; acc[j][2] = b0; acc[j][3] = b1;
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint2 bb = bfrag[((grp * KS + ks) * 8 + j) * 32 + lane];
+          mma_16816(acc[j], a[ks], bb.x, bb.y);
+        }
+#pragma unroll
+      for (int rs = 0; rs < 2; ++rs) {
+        const int gx = x0 + xb + g + rs * 8;
+        if (gx >= w || gy >= h) continue;
+        const size_t pix = ((size_t)b * h + gy) * w + gx;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[2 * j] = acc[j][rs * 2];
+          v[2 * j + 1] = acc[j][rs * 2 + 1];
+        }
+        if (act) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * slope;
+        }
+        if (mask) {
+          float mv[16];
+          const uint4* mp = reinterpret_cast<const uint4*>(mask + pix * mask_c + mask_coff + cbase);
+          unpack8(mp[0], mv);
+          unpack8(mp[1], mv + 8);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = mv[q] > 0.f ? v[q] : v[q] * mask_slope;
+        }
+        uint4* dst = reinterpret_cast<uint4*>(y + pix * cy + y_coff + cbase);
+        dst[0] = pack8(v);
+        dst[1] = pack8(v + 8);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- wide -> thin, GEMM [px] x [9*cw] x [8]
+// block = 16 x 16 pixels, warp = two rows = two m16 tiles sharing every weight fragment.
+__global__ void __launch_bounds__(256)
+wide_to_thin_mma_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wgt,
+                        const float* __restrict__ bias, float* __restrict__ y, int n, int h, int w, int cw,
+                        int cx, int x_coff, int cs, int transpose_w, const float* __restrict__ inv_std,
+                        float out_scale) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  const int chunks = cw / 8, kcs = cw / 16;
+  uint4* tile = reinterpret_cast<uint4*>(dsm);                                   // [324][chunks], swizzled
+  uint2* bfrag = reinterpret_cast<uint2*>(dsm + (size_t)324 * chunks * 16);      // [9][kcs][32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < 9 * kcs * 32; i += 256) {
+    const int l = i & 31, kc = (i >> 5) % kcs, tap = i / (32 * kcs);
+    const int gg = l >> 2, tt = l & 3;
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = kc * 16 + 2 * tt + (q & 1) + (q >> 1) * 8;   // wide channel
+      float r = 0.f;
+      if (gg < cs)
+        r = transpose_w ? wgt[((size_t)j * cs + gg) * 9 + (8 - tap)] : wgt[((size_t)gg * cw + j) * 9 + tap];
+      v[q] = r;
+    }
+    bfrag[i] = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
+  }
+  const int tiles_x = (w + 15) / 16, tiles_y = (h + 15) / 16;
+  const int b = blockIdx.x / (tiles_x * tiles_y);
+  const int tr = blockIdx.x % (tiles_x * tiles_y);
+  const int x0 = (tr % tiles_x) * 16, y0 = (tr / tiles_x) * 16;
+  const int swz_mask = chunks >= 8 ? 7 : (chunks - 1);
+  for (int i = tid; i < 324 * chunks; i += 256) {
+    const int ch = i % chunks, pix = i / chunks;
+    const int px = pix % 18, py = pix / 18;
+    const int gx = x0 + px - 1, gy = y0 + py - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (gx >= 0 && gx < w && gy >= 0 && gy < h)
+      v = *reinterpret_cast<const uint4*>(x + (((size_t)b * h + gy) * w + gx) * cx + x_coff + ch * 8);
+    tile[pix * chunks + (ch ^ (px & swz_mask))] = v;
+  }
+  __syncthreads();
+  float acc[2][4];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
+  const uint32_t tile_s = smem_addr(tile);
+  const int mi = lane >> 3, lr = lane & 7;
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3, dx = tap % 3;
+    const int px = lr + (mi & 1) * 8 + dx;
+    const int sw = px & swz_mask;
+    const int pix0 = (2 * warp + dy) * 18 + px;
+    for (int kc = 0; kc < kcs; ++kc) {
+      const int chunk = (kc * 2 + (mi >> 1)) ^ sw;
+      uint32_t a0[4], a1[4];
+      ldsm_x4(a0, tile_s + (uint32_t)((pix0 * chunks + chunk) * 16));
+      ldsm_x4(a1, tile_s + (uint32_t)(((pix0 + 18) * chunks + chunk) * 16));
+      const uint2 bb = bfrag[(tap * kcs + kc) * 32 + lane];
+      mma_16816(acc[0], a0, bb.x, bb.y);
+      mma_16816(acc[1], a1, bb.x, bb.y);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int gy = y0 + 2 * warp + r;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int co = 2 * t + (q & 1);
+      const int gx = x0 + g + (q >> 1) * 8;
+      if (co >= cs || gx >= w || gy >= h) continue;
+      float v = acc[r][q] + (bias ? bias[co] : 0.f);
+      if (inv_std) v *= inv_std[co];
+      y[(((size_t)b * cs + co) * h + gy) * w + gx] = v * out_scale;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- weight gradient, GEMM [64] x [px] x [CS*9 + 1]
+// A = wide^T (ldmatrix.trans from the [pixel][channel] row tile), B = shifted thin values (+ a column of ones
+// that yields the wide-side bias gradient), K = the pixels of one image row per block iteration.
+template <int CS>
+__global__ void __launch_bounds__(256)
+thin_wgrad_mma_kernel(const float* __restrict__ thin, const __nv_bfloat16* __restrict__ wide,
+                      float* __restrict__ dw, float* __restrict__ dbias_wide, int n, int h, int w, int w16,
+                      int cw, int cwide_buf, int wide_coff, int wide_is_out) {
+  constexpr int NC = CS * 9 + 1;          // used columns (the last one is the ones column)
+  constexpr int NT = (NC + 7) / 8;
+  extern __shared__ __align__(16) uint8_t dsm[];
+  const int wp = w16 + 2;
+  uint4* tile = reinterpret_cast<uint4*>(dsm);                               // [w16][8], swizzled
+  float* rows = reinterpret_cast<float*>(dsm + (size_t)w16 * 128);          // [CS][3][wp]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int sign = wide_is_out ? 1 : -1;
+  const int jbase = blockIdx.y * 64;
+  int off[NT];   // >= 0: offset into rows ; -1: ones ; -2: zero
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int nn = j * 8 + g;
+    if (nn < CS * 9) {
+      const int ci = nn / 9, ky = (nn % 9) / 3, kx = nn % 3;
+      off[j] = (ci * 3 + 1 + sign * (ky - 1)) * wp + sign * (kx - 1) + 1;
+    } else {
+      off[j] = nn == CS * 9 ? -1 : -2;
+    }
+  }
+  float acc[4][NT][4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.f;
+  const uint32_t tile_s = smem_addr(tile);
+  const int mi = lane >> 3, lr = lane & 7;
+  const int total_rows = n * h;
+  for (int row = blockIdx.x; row < total_rows; row += gridDim.x) {
+    const int b = row / h, yy = row % h;
+    __syncthreads();
+    for (int i = tid; i < CS * 3 * wp; i += 256) {
+      const int px = i % wp, r = (i / wp) % 3, ci = i / (3 * wp);
+      const int gy = yy + (r - 1), gx = px - 1;
+      float v = 0.f;
+      if (gx >= 0 && gx < w && gy >= 0 && gy < h) v = thin[(((size_t)b * CS + ci) * h + gy) * w + gx];
+      rows[i] = v;
+    }
+    const __nv_bfloat16* wrow = wide + ((size_t)b * h + yy) * w * cwide_buf + wide_coff + jbase;
+    for (int i = tid; i < w16 * 8; i += 256) {
+      const int ch = i & 7, px = i >> 3;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (px < w) v = *reinterpret_cast<const uint4*>(wrow + (size_t)px * cwide_buf + ch * 8);
+      tile[px * 8 + (ch ^ (px & 7))] = v;
+    }
+    __syncthreads();
+    for (int p0 = warp * 16; p0 < w16; p0 += 128) {
+      uint32_t bq[NT][2];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        if (off[j] >= 0) {
+          const float* rp = rows + off[j] + p0 + 2 * t;
+          bq[j][0] = pack2(rp[0], rp[1]);
+          bq[j][1] = pack2(rp[8], rp[9]);
+        } else {
+          bq[j][0] = bq[j][1] = off[j] == -1 ? 0x3F803F80u : 0u;
+        }
+      }
+      const int px = p0 + lr + (mi >> 1) * 8;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        uint32_t a[4];
+        ldsm_x4_trans(a, tile_s + (uint32_t)((px * 8 + ((m * 2 + (mi & 1)) ^ (px & 7))) * 16));
+#pragma unroll
+        for (int j = 0; j < NT; ++j) mma_16816(acc[m][j], a, bq[j][0], bq[j][1]);
+      }
+    }
+  }
+  // cross-warp reduction in shared memory (the row tile is dead now), then one atomic per output
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(dsm);   // [64][NT*8 + 1]
+  constexpr int RS = NT * 8 + 1;
+  for (int i = tid; i < 64 * RS; i += 256) red[i] = 0.f;
+  __syncthreads();
+  for (int wi = 0; wi < 8; ++wi) {
+    if (warp == wi) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            red[(m * 16 + g + (q >> 1) * 8) * RS + j * 8 + 2 * t + (q & 1)] += acc[m][j][q];
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < 64 * NC; i += 256) {
+    const int m = i / NC, nn = i % NC;
+    const int j = jbase + m;
+    if (j >= cw) continue;
+    const float s = red[m * RS + nn];
+    if (nn < CS * 9) {
+      const int ci = nn / 9, tp = nn % 9;
+      const size_t idx = wide_is_out ? ((size_t)j * CS + ci) * 9 + tp : ((size_t)ci * cw + j) * 9 + tp;
+      atomicAdd(dw + idx, s);
+    } else if (dbias_wide) {
+      atomicAdd(dbias_wide + j, s);
+    }
+  }
+}
+
 __global__ void plane_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int n, int c,
                                  long long hw) {
   const int ch = blockIdx.y;
@@ -292,6 +638,22 @@ int b200_conv3x3_thin_to_wide(const float* x, const float* w_oihw, const float* 
   B200_REQUIRE(cs >= 1 && cs <= kMaxThin, "thin_to_wide: thin channels %d not in 1..4", cs);
   B200_REQUIRE(cw % 8 == 0 && cy % 8 == 0 && y_coff % 8 == 0, "thin_to_wide: wide channels must be multiples of 8");
   const int blocks = n * ((w + 31) / 32) * ((h + 7) / 8);
+  if (cw % 64 == 0 && cw <= 256) {
+    const size_t fsm = (size_t)(cw / 64) * ((cs * 9 + 15) / 16) * 256 * sizeof(uint2);
+#define LAUNCH_TWM(CS)                                                                           \
+  thin_to_wide_mma_kernel<CS><<<blocks, 256, fsm, as_stream(stream)>>>(                          \
+      x, w_oihw, bias, (bf16*)y, n, h, w, cw, cy, y_coff, transpose_w, mean, stdv, act, slope, \
+      (const bf16*)mask, mask_c, mask_coff, mask_slope)
+    switch (cs) {
+      case 1: LAUNCH_TWM(1); break;
+      case 2: LAUNCH_TWM(2); break;
+      case 3: LAUNCH_TWM(3); break;
+      default: LAUNCH_TWM(4); break;
+    }
+#undef LAUNCH_TWM
+    B200_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = (size_t)cs * 9 * cw * sizeof(float);
   B200_REQUIRE(smem <= 40 * 1024, "thin_to_wide: cw too large");
 #define LAUNCH_TW(CS)                                                                            \
@@ -318,6 +680,20 @@ int b200_conv3x3_wide_to_thin(const void* x, const float* w_oihw, const float* b
                "wide_to_thin: wide channels must be multiples of 8 and <= 128");
   const int chunks = cw / 8;
   B200_REQUIRE((chunks & (chunks - 1)) == 0, "wide_to_thin: cw/8 must be a power of two");
+  const int blocks_m = n * ((w + 15) / 16) * ((h + 15) / 16);
+  if (cw % 16 == 0) {
+    const size_t msm = (size_t)324 * chunks * 16 + (size_t)9 * (cw / 16) * 32 * sizeof(uint2);
+    static size_t msm_set = 0;
+    if (msm > 48 * 1024 && msm > msm_set) {
+      B200_CHECK_CUDA(cudaFuncSetAttribute(wide_to_thin_mma_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+      msm_set = msm;
+    }
+    wide_to_thin_mma_kernel<<<blocks_m, 256, msm, as_stream(stream)>>>(
+        (const bf16*)x, w_oihw, bias, y, n, h, w, cw, cx, x_coff, cs, transpose_w, inv_std, out_scale);
+    B200_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = (size_t)324 * chunks * 16 + (size_t)9 * cw * 16;
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
@@ -339,10 +715,31 @@ int b200_conv3x3_thin_wgrad(const float* thin, const void* wide, float* dw, floa
   (void)mean;
   (void)stdv;
   B200_REQUIRE(cs >= 1 && cs <= kMaxThin, "thin_wgrad: thin channels %d not in 1..4", cs);
-  const size_t smem = (size_t)cs * 3 * (w + 2) * sizeof(float);
-  B200_REQUIRE(smem <= 48 * 1024, "thin_wgrad: row too wide");
   int gx = n * h < 2 * sm_count() ? n * h : 2 * sm_count();
   dim3 grid(gx, (cw + 63) / 64);
+  const int w16 = (w + 15) / 16 * 16;
+  const size_t msm = (size_t)w16 * 128 + (size_t)cs * 3 * (w16 + 2) * sizeof(float);
+  if (cw % 64 == 0 && cwide_buf % 8 == 0 && wide_coff % 8 == 0 && msm <= 48 * 1024 && msm >= 64 * 41 * 4) {
+#define LAUNCH_WGM(CS)                                                              \
+  thin_wgrad_mma_kernel<CS><<<grid, 256, msm, as_stream(stream)>>>(                 \
+      thin, (const bf16*)wide, dw, dbias_wide, n, h, w, w16, cw, cwide_buf, wide_coff, wide_is_out)
+    switch (cs) {
+      case 1: LAUNCH_WGM(1); break;
+      case 2: LAUNCH_WGM(2); break;
+      case 3: LAUNCH_WGM(3); break;
+      default: LAUNCH_WGM(4); break;
+    }
+#undef LAUNCH_WGM
+    B200_LAUNCH_CHECK();
+    if (dbias_thin) {
+      dim3 g2(32, cs);
+      plane_sum_kernel<<<g2, 256, 0, as_stream(stream)>>>(thin, dbias_thin, n, cs, (long long)h * w);
+      B200_LAUNCH_CHECK();
+    }
+    return 0;
+  }
+  const size_t smem = (size_t)cs * 3 * (w + 2) * sizeof(float);
+  B200_REQUIRE(smem <= 48 * 1024, "thin_wgrad: row too wide");
 #define LAUNCH_WG(CS)                                                               \
   thin_wgrad_kernel<CS><<<grid, 256, smem, as_stream(stream)>>>(                    \
       thin, (const bf16*)wide, dw, dbias_wide, n, h, w, cw, cwide_buf, wide_coff, wide_is_out)
