@@ -1,6 +1,7 @@
 #include "common.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -19,6 +20,15 @@ EncodeTiled_t get_encode_tiled() {
       fn = reinterpret_cast<EncodeTiled_t>(p);
   });
   return fn;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("B200_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
 }
 
 int sm_count() {

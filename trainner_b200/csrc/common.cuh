@@ -58,4 +58,33 @@ int make_tensor_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* d
 
 inline cudaStream_t as_stream(b200_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch: every kernel of the library is launched with the
+// programmatic-stream-serialization attribute, calls pdl_trigger() on entry and pdl_wait() before its
+// first access to global memory, so that the launch latency and prologue (barrier init, TMEM
+// allocation, descriptor prefetch) of kernel N+1 overlap the tail of kernel N.  griddepcontrol.wait
+// returns only when the preceding grid has completed and flushed, so ordering is unchanged; because
+// every kernel waits, completion stays transitive along the stream.  B200_PDL=0 turns the attribute off.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 }  // namespace b200

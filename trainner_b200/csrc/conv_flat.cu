@@ -219,6 +219,7 @@ __device__ __forceinline__ void flat_issue_chunk(const FlatParams& p, const uint
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_flat_kernel(const __grid_constant__ FlatParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -257,6 +258,7 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  pdl_wait();   // everything above overlapped the previous kernel's tail
   if (warp == 0) DBG_T(1);
 
   if (warp == 0) {
@@ -423,6 +425,8 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
 __global__ void pad_copy_kernel(__nv_bfloat16* __restrict__ dst, int dst_c, int dst_coff,
                                 const __nv_bfloat16* __restrict__ src, int src_c, int src_coff, int n,
                                 int h, int w, int c) {
+  pdl_trigger();
+  pdl_wait();
   const int cv = c / 8;
   const long long total = (long long)n * h * w * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -444,6 +448,8 @@ __global__ void unpad_add_kernel(__nv_bfloat16* __restrict__ dst, int dst_c,
                                  const __nv_bfloat16* __restrict__ src, int src_c, int src_coff,
                                  const __nv_bfloat16* __restrict__ add, int add_c, int n, int h, int w,
                                  int c) {
+  pdl_trigger();
+  pdl_wait();
   const int cv = c / 8;
   const long long total = (long long)n * h * w * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -591,7 +597,7 @@ extern "C" int b200_conv3x3_flat(const b200_flat_desc* d, const void* x, const v
   const int sms = sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024;
-  conv_flat_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(p);
+  ::b200::launch_kernel(conv_flat_kernel, grid, kThreads, smem, as_stream(stream), p);
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -603,7 +609,7 @@ extern "C" int b200_pad_copy(void* dst_flat, int32_t dst_c, int32_t dst_coff, co
                "b200_pad_copy: channels must be multiples of 8");
   long long total = (long long)n * h * w * (c / 8);
   int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  pad_copy_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, as_stream(stream)>>>(
+  ::b200::launch_kernel(pad_copy_kernel, blocks < 1 ? 1 : blocks, 256, 0, as_stream(stream), 
       (__nv_bfloat16*)dst_flat, dst_c, dst_coff, (const __nv_bfloat16*)src_dense, src_c, src_coff, n, h, w, c);
   B200_LAUNCH_CHECK();
   return 0;
@@ -616,7 +622,7 @@ extern "C" int b200_unpad_add(void* dst_dense, int32_t dst_c, const void* src_fl
                "b200_unpad_add: channels must be multiples of 8");
   long long total = (long long)n * h * w * (c / 8);
   int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  unpad_add_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, as_stream(stream)>>>(
+  ::b200::launch_kernel(unpad_add_kernel, blocks < 1 ? 1 : blocks, 256, 0, as_stream(stream), 
       (__nv_bfloat16*)dst_dense, dst_c, (const __nv_bfloat16*)src_flat, src_c, src_coff,
       (const __nv_bfloat16*)add_dense, add_c, n, h, w, c);
   B200_LAUNCH_CHECK();

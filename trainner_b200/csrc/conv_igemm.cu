@@ -160,6 +160,7 @@ __device__ __forceinline__ void epilogue_columns(const IgemmParams& p, const uin
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -192,6 +193,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  pdl_wait();   // everything above overlapped the previous kernel's tail
   const int k_iters = p.ntaps * p.k_chunks;
 
   if (warp == 0) {
@@ -402,6 +404,7 @@ __device__ __forceinline__ void epi256_store(const IgemmParams& p, const uint32_
 
 __global__ void __launch_bounds__(kThreads256, 1)
 conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -433,6 +436,7 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  pdl_wait();   // everything above overlapped the previous kernel's tail
   const int k_iters = p.ntaps * p.k_chunks;
 
   if (warp == 0) {
@@ -712,9 +716,9 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   if (use256)
-    conv_igemm256_kernel<<<grid, kThreads256, smem, as_stream(stream)>>>(p);
+    ::b200::launch_kernel(conv_igemm256_kernel, grid, kThreads256, smem, as_stream(stream), p);
   else
-    conv_igemm_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(p);
+    ::b200::launch_kernel(conv_igemm_kernel, grid, kThreads, smem, as_stream(stream), p);
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -35,6 +35,7 @@ struct WgradParams {
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -62,6 +63,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  pdl_wait();   // everything above overlapped the previous kernel's tail
   const int acc_cols = (p.BN + 31) & ~31;
 
   // item -> (t, mb, nb, ks)
@@ -189,6 +191,8 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
 // Per-channel column sum of an NHWC bf16 slice: db[c] += scale * sum_p dy[p, coff + c]
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
                               long long npix, int cdy, int coff, int c, float scale) {
+  pdl_trigger();
+  pdl_wait();
   // block: 256 threads = 8 pixel lanes x 32 channel lanes; grid.y over channel groups of 32
   const int cl = threadIdx.x & 31;
   const int pl = threadIdx.x >> 5;
@@ -213,6 +217,8 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __res
 // floats (coalesced across the warp along the source's fastest dimension) instead of one strided gather
 // per tap, and every tap plane of the destination is written with consecutive columns.
 __global__ void pack_weights_kernel(const b200_pack_entry* __restrict__ table, int count) {
+  pdl_trigger();
+  pdl_wait();
   const b200_pack_entry e = table[blockIdx.y];
   const long long total = (long long)e.rows_pad * e.cols_pad;
   const long long plane = total;
@@ -233,6 +239,8 @@ __global__ void pack_weights_kernel(const b200_pack_entry* __restrict__ table, i
 }
 
 __global__ void pack_cat_kernel(const b200_packcat_entry* __restrict__ table) {
+  pdl_trigger();
+  pdl_wait();
   const b200_packcat_entry e = table[blockIdx.y];
   const long long total = (long long)e.n_rows * e.cout;
   const size_t plane = (size_t)e.rows_pad * e.cols_pad;
@@ -263,7 +271,7 @@ extern "C" int b200_pack_cat(const b200_packcat_entry* table_dev, int32_t count,
   if (bx < 1) bx = 1;
   if (bx > 32) bx = 32;
   dim3 grid(bx, count);
-  pack_cat_kernel<<<grid, 256, 0, as_stream(stream)>>>(table_dev);
+  ::b200::launch_kernel(pack_cat_kernel, grid, 256, 0, as_stream(stream), table_dev);
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -277,7 +285,7 @@ extern "C" int b200_conv_wgrad(const b200_wgrad_desc* d, const void* x, const vo
   if (dbias) {
     dim3 grid((unsigned)((npix + 8 * 64 - 1) / (8 * 64) < 1024 ? (npix + 8 * 64 - 1) / (8 * 64) : 1024),
               (d->cout + 31) / 32);
-    colsum_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dy),
+    ::b200::launch_kernel(colsum_kernel, grid, 256, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(dy),
                                                       dbias, npix, d->cdy, d->dy_coff, d->cout,
                                                       d->scale);
     B200_LAUNCH_CHECK();
@@ -349,7 +357,7 @@ extern "C" int b200_conv_wgrad(const b200_wgrad_desc* d, const void* x, const vo
   }
   const int grid = p.total_items < sms ? p.total_items : sms;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-  conv_wgrad_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(p);
+  ::b200::launch_kernel(conv_wgrad_kernel, grid, kThreads, smem, as_stream(stream), p);
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -362,7 +370,7 @@ extern "C" int b200_pack_weights(const b200_pack_entry* table_dev, int32_t count
   if (bx < 1) bx = 1;
   if (bx > 64) bx = 64;
   dim3 grid(bx, count);
-  pack_weights_kernel<<<grid, 256, 0, as_stream(stream)>>>(table_dev, count);
+  ::b200::launch_kernel(pack_weights_kernel, grid, 256, 0, as_stream(stream), table_dev, count);
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -44,6 +44,8 @@ __global__ void bn_reduce_kernel(const __nv_bfloat16* __restrict__ z,
                                  const float* __restrict__ mean_invstd,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float* __restrict__ sums, long long npix, int c, float slope) {
+  pdl_trigger();
+  pdl_wait();
   const int vec_per_pix = c / 8;
   const long long total_vec = npix * vec_per_pix;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -120,6 +122,8 @@ __global__ void bn_reduce_kernel(const __nv_bfloat16* __restrict__ z,
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, float* __restrict__ mean_invstd,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long npix, int c, float momentum, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   const double n = (double)npix;
@@ -142,6 +146,8 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ sums, __nv_bfloat16* __restrict__ out,
                                 long long npix, int c, float slope) {
+  pdl_trigger();
+  pdl_wait();
   const int vec_per_pix = c / 8;
   const long long total_vec = npix * vec_per_pix;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -198,6 +204,8 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z,
 }
 
 __global__ void add_small_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] += src[i];
 }
@@ -205,6 +213,8 @@ __global__ void add_small_kernel(float* __restrict__ dst, const float* __restric
 // ------------------------------------------------------------------ MaxPool 2x2
 __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                int n, int h, int w, int c) {
+  pdl_trigger();
+  pdl_wait();
   const int ho = h / 2, wo = w / 2, cv = c / 8;
   const long long total = (long long)n * ho * wo * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -236,6 +246,8 @@ __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x,
                                    const __nv_bfloat16* __restrict__ dy,
                                    __nv_bfloat16* __restrict__ dx, int n, int h, int w, int c) {
+  pdl_trigger();
+  pdl_wait();
   const int ho = h / 2, wo = w / 2, cv = c / 8;
   const long long total = (long long)n * ho * wo * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -275,6 +287,8 @@ __global__ void sumpool_mask_kernel(const __nv_bfloat16* __restrict__ dy,
                                     const __nv_bfloat16* __restrict__ mask,
                                     __nv_bfloat16* __restrict__ dx, int n, int h, int w, int c,
                                     float slope) {
+  pdl_trigger();
+  pdl_wait();
   // dx: [n,h,w,c]; dy: [n,2h,2w,c]
   const int cv = c / 8;
   const long long total = (long long)n * h * w * cv;
@@ -310,6 +324,8 @@ __global__ void sumpool_mask_kernel(const __nv_bfloat16* __restrict__ dy,
 __global__ void lrelu_mask_mul_kernel(const __nv_bfloat16* __restrict__ g,
                                       const __nv_bfloat16* __restrict__ y,
                                       __nv_bfloat16* __restrict__ out, long long nvec, float slope) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     float a[8], t[8];
@@ -339,6 +355,8 @@ template <typename T>
 __global__ void l1_loss_kernel(const T* __restrict__ a, const T* __restrict__ b,
                                float* __restrict__ loss_out, T* __restrict__ grad_a, long long numel,
                                float scale) {
+  pdl_trigger();
+  pdl_wait();
   // scale = weight / numel
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < numel;
@@ -362,6 +380,8 @@ __global__ void l1_loss_kernel(const T* __restrict__ a, const T* __restrict__ b,
 // ------------------------------------------------------------------ layout conversion
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n,
                                     int c, int h, int w, int cy, int coff) {
+  pdl_trigger();
+  pdl_wait();
   const long long hw = (long long)h * w;
   const long long total = (long long)n * hw * c;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -374,6 +394,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
 }
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int n,
                                     int c, int h, int w, int cx, int coff) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)n * c * h * w;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -387,6 +409,8 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* 
 __global__ void add_slice_kernel(__nv_bfloat16* __restrict__ dst, int dst_c, int dst_coff,
                                  const __nv_bfloat16* __restrict__ src, int src_c, int src_coff,
                                  long long npix, int c) {
+  pdl_trigger();
+  pdl_wait();
   const int cv = c / 8;
   const long long total = npix * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -403,6 +427,8 @@ __global__ void add_slice_kernel(__nv_bfloat16* __restrict__ dst, int dst_c, int
   }
 }
 __global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     dst[i] += src[i];
@@ -429,7 +455,7 @@ extern "C" {
 int b200_bn_stats(const void* z, float* stats, int64_t npix, int32_t c, b200_stream_t stream) {
   B200_REQUIRE(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "b200_bn_stats: c/8 must be a power of two <= 256 (c=%d)", c);
   B200_CHECK_CUDA(cudaMemsetAsync(stats, 0, 2 * c * sizeof(float), as_stream(stream)));
-  bn_reduce_kernel<0><<<bn_grid(npix, c, 4), 256, 16 * 256 * sizeof(float), as_stream(stream)>>>(
+  ::b200::launch_kernel(bn_reduce_kernel<0>, bn_grid(npix, c, 4), 256, 16 * 256 * sizeof(float), as_stream(stream), 
       (const bf16*)z, nullptr, nullptr, nullptr, nullptr, stats, npix, c, 0.f);
   B200_LAUNCH_CHECK();
   return 0;
@@ -438,7 +464,7 @@ int b200_bn_stats(const void* z, float* stats, int64_t npix, int32_t c, b200_str
 int b200_bn_finalize(const float* stats, float* mean_invstd, float* running_mean,
                      float* running_var, int64_t npix, int32_t c, float momentum, float eps,
                      b200_stream_t stream) {
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(
+  ::b200::launch_kernel(bn_finalize_kernel, (c + 127) / 128, 128, 0, as_stream(stream), 
       stats, mean_invstd, running_mean, running_var, npix, c, momentum, eps);
   B200_LAUNCH_CHECK();
   return 0;
@@ -448,7 +474,7 @@ int b200_bn_apply_lrelu(const void* z, const float* mean_invstd, const float* ga
                         const float* beta, void* a, int64_t npix, int32_t c, float slope,
                         b200_stream_t stream) {
   B200_REQUIRE(c % 8 == 0, "b200_bn_apply_lrelu: c must be a multiple of 8");
-  bn_apply_kernel<0><<<bn_grid(npix, c, 2), 256, 0, as_stream(stream)>>>(
+  ::b200::launch_kernel(bn_apply_kernel<0>, bn_grid(npix, c, 2), 256, 0, as_stream(stream), 
       (const bf16*)z, nullptr, mean_invstd, gamma, beta, nullptr, (bf16*)a, npix, c, slope);
   B200_LAUNCH_CHECK();
   return 0;
@@ -459,7 +485,7 @@ int b200_bn_bwd_reduce(const void* z, const void* da, const float* mean_invstd, 
                        b200_stream_t stream) {
   B200_REQUIRE(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "b200_bn_bwd_reduce: c/8 must be a power of two <= 256 (c=%d)", c);
   B200_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * c * sizeof(float), as_stream(stream)));
-  bn_reduce_kernel<1><<<bn_grid(npix, c, 4), 256, 16 * 256 * sizeof(float), as_stream(stream)>>>(
+  ::b200::launch_kernel(bn_reduce_kernel<1>, bn_grid(npix, c, 4), 256, 16 * 256 * sizeof(float), as_stream(stream), 
       (const bf16*)z, (const bf16*)da, mean_invstd, gamma, beta, sums, npix, c, slope);
   B200_LAUNCH_CHECK();
   return 0;
@@ -468,15 +494,15 @@ int b200_bn_bwd_reduce(const void* z, const void* da, const float* mean_invstd, 
 int b200_bn_bwd_apply(const void* z, const void* da, const float* mean_invstd, const float* gamma,
                       const float* beta, const float* sums, void* dz, float* dgamma, float* dbeta,
                       int64_t npix, int32_t c, float slope, b200_stream_t stream) {
-  bn_apply_kernel<1><<<bn_grid(npix, c, 2), 256, 0, as_stream(stream)>>>(
+  ::b200::launch_kernel(bn_apply_kernel<1>, bn_grid(npix, c, 2), 256, 0, as_stream(stream), 
       (const bf16*)z, (const bf16*)da, mean_invstd, gamma, beta, sums, (bf16*)dz, npix, c, slope);
   B200_LAUNCH_CHECK();
   if (dgamma) {
-    add_small_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(dgamma, sums + c, c);
+    ::b200::launch_kernel(add_small_kernel, (c + 127) / 128, 128, 0, as_stream(stream), dgamma, sums + c, c);
     B200_LAUNCH_CHECK();
   }
   if (dbeta) {
-    add_small_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(dbeta, sums, c);
+    ::b200::launch_kernel(add_small_kernel, (c + 127) / 128, 128, 0, as_stream(stream), dbeta, sums, c);
     B200_LAUNCH_CHECK();
   }
   return 0;
@@ -486,7 +512,7 @@ int b200_maxpool2x2(const void* x, void* y, int32_t n, int32_t h, int32_t w, int
                     b200_stream_t stream) {
   B200_REQUIRE(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "b200_maxpool2x2: bad shape");
   const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
-  maxpool_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const bf16*)x, (bf16*)y, n, h,
+  ::b200::launch_kernel(maxpool_kernel, grid_for(total, 256), 256, 0, as_stream(stream), (const bf16*)x, (bf16*)y, n, h,
                                                                      w, c);
   B200_LAUNCH_CHECK();
   return 0;
@@ -496,7 +522,7 @@ int b200_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int32_t n, int3
                         int32_t c, b200_stream_t stream) {
   B200_REQUIRE(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "b200_maxpool2x2_bwd: bad shape");
   const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
-  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+  ::b200::launch_kernel(maxpool_bwd_kernel, grid_for(total, 256), 256, 0, as_stream(stream), 
       (const bf16*)x, (const bf16*)dy, (bf16*)dx, n, h, w, c);
   B200_LAUNCH_CHECK();
   return 0;
@@ -506,7 +532,7 @@ int b200_sumpool2x2_mask(const void* dy, const void* mask, void* dx, int32_t n, 
                          int32_t w, int32_t c, float slope, b200_stream_t stream) {
   B200_REQUIRE(c % 8 == 0, "b200_sumpool2x2_mask: bad shape");
   const long long total = (long long)n * h * w * (c / 8);
-  sumpool_mask_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+  ::b200::launch_kernel(sumpool_mask_kernel, grid_for(total, 256), 256, 0, as_stream(stream), 
       (const bf16*)dy, (const bf16*)mask, (bf16*)dx, n, h, w, c, slope);
   B200_LAUNCH_CHECK();
   return 0;
@@ -515,7 +541,7 @@ int b200_sumpool2x2_mask(const void* dy, const void* mask, void* dx, int32_t n, 
 int b200_l1_loss_f32(const float* a, const float* b, float* loss_out, float* grad_a, int64_t numel,
                      float weight, b200_stream_t stream) {
   B200_CHECK_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), as_stream(stream)));
-  l1_loss_kernel<float><<<grid_for(numel, 256, 148 * 4), 256, 0, as_stream(stream)>>>(
+  ::b200::launch_kernel(l1_loss_kernel<float>, grid_for(numel, 256, 148 * 4), 256, 0, as_stream(stream), 
       a, b, loss_out, grad_a, numel, weight / (float)numel);
   B200_LAUNCH_CHECK();
   return 0;
@@ -524,7 +550,7 @@ int b200_l1_loss_f32(const float* a, const float* b, float* loss_out, float* gra
 int b200_l1_loss_bf16(const void* a, const void* b, float* loss_out, void* grad_a, int64_t numel,
                       float weight, b200_stream_t stream) {
   B200_CHECK_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), as_stream(stream)));
-  l1_loss_kernel<bf16><<<grid_for(numel, 256, 148 * 4), 256, 0, as_stream(stream)>>>(
+  ::b200::launch_kernel(l1_loss_kernel<bf16>, grid_for(numel, 256, 148 * 4), 256, 0, as_stream(stream), 
       (const bf16*)a, (const bf16*)b, loss_out, (bf16*)grad_a, numel, weight / (float)numel);
   B200_LAUNCH_CHECK();
   return 0;
@@ -533,7 +559,7 @@ int b200_l1_loss_bf16(const void* a, const void* b, float* loss_out, void* grad_
 int b200_lrelu_mask_mul(const void* g, const void* y, void* out, int64_t numel, float slope,
                         b200_stream_t stream) {
   B200_REQUIRE(numel % 8 == 0, "b200_lrelu_mask_mul: numel must be a multiple of 8");
-  lrelu_mask_mul_kernel<<<grid_for(numel / 8, 256), 256, 0, as_stream(stream)>>>(
+  ::b200::launch_kernel(lrelu_mask_mul_kernel, grid_for(numel / 8, 256), 256, 0, as_stream(stream), 
       (const bf16*)g, (const bf16*)y, (bf16*)out, numel / 8, slope);
   B200_LAUNCH_CHECK();
   return 0;
@@ -541,7 +567,7 @@ int b200_lrelu_mask_mul(const void* g, const void* y, void* out, int64_t numel, 
 
 int b200_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t h, int32_t w,
                                int32_t cy, int32_t y_coff, b200_stream_t stream) {
-  nchw_to_nhwc_kernel<<<grid_for((long long)n * h * w * c, 256), 256, 0, as_stream(stream)>>>(
+  ::b200::launch_kernel(nchw_to_nhwc_kernel, grid_for((long long)n * h * w * c, 256), 256, 0, as_stream(stream), 
       x, (bf16*)y, n, c, h, w, cy, y_coff);
   B200_LAUNCH_CHECK();
   return 0;
@@ -549,7 +575,7 @@ int b200_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, in
 
 int b200_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t n, int32_t c, int32_t h, int32_t w,
                                int32_t cx, int32_t x_coff, b200_stream_t stream) {
-  nhwc_to_nchw_kernel<<<grid_for((long long)n * c * h * w, 256), 256, 0, as_stream(stream)>>>(
+  ::b200::launch_kernel(nhwc_to_nchw_kernel, grid_for((long long)n * c * h * w, 256), 256, 0, as_stream(stream), 
       (const bf16*)x, y, n, c, h, w, cx, x_coff);
   B200_LAUNCH_CHECK();
   return 0;
@@ -559,14 +585,14 @@ int b200_add_slice_bf16(void* dst, int32_t dst_c, int32_t dst_coff, const void* 
                         int32_t src_coff, int64_t npix, int32_t c, b200_stream_t stream) {
   B200_REQUIRE(c % 8 == 0 && dst_c % 8 == 0 && src_c % 8 == 0 && dst_coff % 8 == 0 && src_coff % 8 == 0,
                "b200_add_slice_bf16: channels must be multiples of 8");
-  add_slice_kernel<<<grid_for(npix * (c / 8), 256), 256, 0, as_stream(stream)>>>(
+  ::b200::launch_kernel(add_slice_kernel, grid_for(npix * (c / 8), 256), 256, 0, as_stream(stream), 
       (bf16*)dst, dst_c, dst_coff, (const bf16*)src, src_c, src_coff, npix, c);
   B200_LAUNCH_CHECK();
   return 0;
 }
 
 int b200_add_f32(float* dst, const float* src, int64_t numel, b200_stream_t stream) {
-  add_f32_kernel<<<grid_for(numel, 256), 256, 0, as_stream(stream)>>>(dst, src, numel);
+  ::b200::launch_kernel(add_f32_kernel, grid_for(numel, 256), 256, 0, as_stream(stream), dst, src, numel);
   B200_LAUNCH_CHECK();
   return 0;
 }

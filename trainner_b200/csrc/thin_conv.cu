@@ -39,6 +39,8 @@ thin_to_wide_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
                     const float* __restrict__ mean, const float* __restrict__ stdv, int act,
                     float slope, const __nv_bfloat16* __restrict__ mask, int mask_c, int mask_coff,
                     float mask_slope) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float wsm[];  // [CS*9][cw]
   __shared__ float patch[CS][10][34];
   const int tid = threadIdx.x;
@@ -110,6 +112,8 @@ wide_to_thin_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
                     const float* __restrict__ bias, float* __restrict__ y, int n, int h, int w, int cw,
                     int cx, int x_coff, int cs, int transpose_w, const float* __restrict__ inv_std,
                     float out_scale) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t dsm[];
   const int chunks = cw / 8;
   uint4* tile = reinterpret_cast<uint4*>(dsm);                       // [324][chunks]
@@ -174,6 +178,8 @@ __global__ void __launch_bounds__(256)
 thin_wgrad_kernel(const float* __restrict__ thin, const __nv_bfloat16* __restrict__ wide,
                   float* __restrict__ dw, float* __restrict__ dbias_wide, int n, int h, int w,
                   int cw, int cwide_buf, int wide_coff, int wide_is_out) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float rows[];  // [CS][3][w + 2]
   __shared__ float red[4][64];
   const int tid = threadIdx.x;
@@ -296,6 +302,8 @@ thin_to_wide_mma_kernel(const float* __restrict__ x, const float* __restrict__ w
                         const float* __restrict__ mean, const float* __restrict__ stdv, int act,
                         float slope, const __nv_bfloat16* __restrict__ mask, int mask_c, int mask_coff,
                         float mask_slope) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int KS = (CS * 9 + 15) / 16;
   extern __shared__ uint2 bfrag[];  // [cw/64][KS][8][32]
   __shared__ float patch[CS * 10 * 34];
@@ -414,6 +422,8 @@ wide_to_thin_mma_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
                         const float* __restrict__ bias, float* __restrict__ y, int n, int h, int w, int cw,
                         int cx, int x_coff, int cs, int transpose_w, const float* __restrict__ inv_std,
                         float out_scale) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t dsm[];
   const int chunks = cw / 8, kcs = cw / 16;
   uint4* tile = reinterpret_cast<uint4*>(dsm);                                   // [324][chunks], swizzled
@@ -495,6 +505,8 @@ __global__ void __launch_bounds__(256)
 thin_wgrad_mma_kernel(const float* __restrict__ thin, const __nv_bfloat16* __restrict__ wide,
                       float* __restrict__ dw, float* __restrict__ dbias_wide, int n, int h, int w, int w16,
                       int cw, int cwide_buf, int wide_coff, int wide_is_out) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int NC = CS * 9 + 1;          // used columns (the last one is the ones column)
   constexpr int NT = (NC + 7) / 8;
   extern __shared__ __align__(16) uint8_t dsm[];
@@ -601,6 +613,8 @@ thin_wgrad_mma_kernel(const float* __restrict__ thin, const __nv_bfloat16* __res
 
 __global__ void plane_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int n, int c,
                                  long long hw) {
+  pdl_trigger();
+  pdl_wait();
   const int ch = blockIdx.y;
   float s = 0.f;
   for (int b = 0; b < n; ++b) {
@@ -641,7 +655,7 @@ int b200_conv3x3_thin_to_wide(const float* x, const float* w_oihw, const float* 
   if (cw % 64 == 0 && cw <= 256) {
     const size_t fsm = (size_t)(cw / 64) * ((cs * 9 + 15) / 16) * 256 * sizeof(uint2);
 #define LAUNCH_TWM(CS)                                                                           \
-  thin_to_wide_mma_kernel<CS><<<blocks, 256, fsm, as_stream(stream)>>>(                          \
+  ::b200::launch_kernel(thin_to_wide_mma_kernel<CS>, blocks, 256, fsm, as_stream(stream),                           \
       x, w_oihw, bias, (bf16*)y, n, h, w, cw, cy, y_coff, transpose_w, mean, stdv, act, slope, \
       (const bf16*)mask, mask_c, mask_coff, mask_slope)
     switch (cs) {
@@ -657,7 +671,7 @@ int b200_conv3x3_thin_to_wide(const float* x, const float* w_oihw, const float* 
   const size_t smem = (size_t)cs * 9 * cw * sizeof(float);
   B200_REQUIRE(smem <= 40 * 1024, "thin_to_wide: cw too large");
 #define LAUNCH_TW(CS)                                                                            \
-  thin_to_wide_kernel<CS><<<blocks, 256, smem, as_stream(stream)>>>(                             \
+  ::b200::launch_kernel(thin_to_wide_kernel<CS>, blocks, 256, smem, as_stream(stream),                              \
       x, w_oihw, bias, (bf16*)y, n, h, w, cw, cy, y_coff, transpose_w, mean, stdv, act, slope, \
       (const bf16*)mask, mask_c, mask_coff, mask_slope)
   switch (cs) {
@@ -689,7 +703,7 @@ int b200_conv3x3_wide_to_thin(const void* x, const float* w_oihw, const float* b
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
       msm_set = msm;
     }
-    wide_to_thin_mma_kernel<<<blocks_m, 256, msm, as_stream(stream)>>>(
+    ::b200::launch_kernel(wide_to_thin_mma_kernel, blocks_m, 256, msm, as_stream(stream), 
         (const bf16*)x, w_oihw, bias, y, n, h, w, cw, cx, x_coff, cs, transpose_w, inv_std, out_scale);
     B200_LAUNCH_CHECK();
     return 0;
@@ -702,7 +716,7 @@ int b200_conv3x3_wide_to_thin(const void* x, const float* w_oihw, const float* b
     smem_set = smem;
   }
   const int blocks = n * ((w + 15) / 16) * ((h + 15) / 16);
-  wide_to_thin_kernel<<<blocks, 256, smem, as_stream(stream)>>>(
+  ::b200::launch_kernel(wide_to_thin_kernel, blocks, 256, smem, as_stream(stream), 
       (const bf16*)x, w_oihw, bias, y, n, h, w, cw, cx, x_coff, cs, transpose_w, inv_std, out_scale);
   B200_LAUNCH_CHECK();
   return 0;
@@ -721,7 +735,7 @@ int b200_conv3x3_thin_wgrad(const float* thin, const void* wide, float* dw, floa
   const size_t msm = (size_t)w16 * 128 + (size_t)cs * 3 * (w16 + 2) * sizeof(float);
   if (cw % 64 == 0 && cwide_buf % 8 == 0 && wide_coff % 8 == 0 && msm <= 48 * 1024 && msm >= 64 * 41 * 4) {
 #define LAUNCH_WGM(CS)                                                              \
-  thin_wgrad_mma_kernel<CS><<<grid, 256, msm, as_stream(stream)>>>(                 \
+  ::b200::launch_kernel(thin_wgrad_mma_kernel<CS>, grid, 256, msm, as_stream(stream),                  \
       thin, (const bf16*)wide, dw, dbias_wide, n, h, w, w16, cw, cwide_buf, wide_coff, wide_is_out)
     switch (cs) {
       case 1: LAUNCH_WGM(1); break;
@@ -733,7 +747,7 @@ int b200_conv3x3_thin_wgrad(const float* thin, const void* wide, float* dw, floa
     B200_LAUNCH_CHECK();
     if (dbias_thin) {
       dim3 g2(32, cs);
-      plane_sum_kernel<<<g2, 256, 0, as_stream(stream)>>>(thin, dbias_thin, n, cs, (long long)h * w);
+      ::b200::launch_kernel(plane_sum_kernel, g2, 256, 0, as_stream(stream), thin, dbias_thin, n, cs, (long long)h * w);
       B200_LAUNCH_CHECK();
     }
     return 0;
@@ -741,7 +755,7 @@ int b200_conv3x3_thin_wgrad(const float* thin, const void* wide, float* dw, floa
   const size_t smem = (size_t)cs * 3 * (w + 2) * sizeof(float);
   B200_REQUIRE(smem <= 48 * 1024, "thin_wgrad: row too wide");
 #define LAUNCH_WG(CS)                                                               \
-  thin_wgrad_kernel<CS><<<grid, 256, smem, as_stream(stream)>>>(                    \
+  ::b200::launch_kernel(thin_wgrad_kernel<CS>, grid, 256, smem, as_stream(stream),                     \
       thin, (const bf16*)wide, dw, dbias_wide, n, h, w, cw, cwide_buf, wide_coff, wide_is_out)
   switch (cs) {
     case 1: LAUNCH_WG(1); break;
@@ -753,7 +767,7 @@ int b200_conv3x3_thin_wgrad(const float* thin, const void* wide, float* dw, floa
   B200_LAUNCH_CHECK();
   if (dbias_thin) {
     dim3 g2(32, cs);
-    plane_sum_kernel<<<g2, 256, 0, as_stream(stream)>>>(thin, dbias_thin, n, cs, (long long)h * w);
+    ::b200::launch_kernel(plane_sum_kernel, g2, 256, 0, as_stream(stream), thin, dbias_thin, n, cs, (long long)h * w);
     B200_LAUNCH_CHECK();
   }
   return 0;

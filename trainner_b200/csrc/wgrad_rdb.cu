@@ -48,6 +48,7 @@ __device__ __forceinline__ void item_decode(int item, int& r, int& dy, int& type
 
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_rdb_kernel(const __grid_constant__ RdbItemParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -73,6 +74,7 @@ wgrad_rdb_kernel(const __grid_constant__ RdbItemParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  pdl_wait();   // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -226,6 +228,8 @@ wgrad_rdb_kernel(const __grid_constant__ RdbItemParams p) {
 }
 
 __global__ void colsum_multi_kernel(const b200_colsum_entry* __restrict__ table) {
+  pdl_trigger();
+  pdl_wait();
   const b200_colsum_entry e = table[blockIdx.y];
   const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(e.src);
   // 256 threads = 8 pixel lanes x 32 channel lanes; channel groups of 32 looped
@@ -258,7 +262,7 @@ extern "C" int b200_colsum_multi(const b200_colsum_entry* table_dev, int32_t cou
   if (count <= 0) return 0;
   B200_REQUIRE(table_dev, "b200_colsum_multi: null table");
   dim3 grid(32, count);
-  colsum_multi_kernel<<<grid, 256, 0, as_stream(stream)>>>(table_dev);
+  ::b200::launch_kernel(colsum_multi_kernel, grid, 256, 0, as_stream(stream), table_dev);
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -308,7 +312,7 @@ extern "C" int b200_wgrad_rdb(const void* maps_dev, const b200_wgrad_rdb_entry* 
   p.gc = gc;
   const int sms = sm_count();
   const int grid = p.total_items < sms ? p.total_items : sms;
-  wgrad_rdb_kernel<<<grid, kThreads, kSmemBytes, as_stream(stream)>>>(p);
+  ::b200::launch_kernel(wgrad_rdb_kernel, grid, kThreads, kSmemBytes, as_stream(stream), p);
   B200_LAUNCH_CHECK();
   return 0;
 }
