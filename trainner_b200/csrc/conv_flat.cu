@@ -43,7 +43,7 @@ struct FlatParams {
   int a_stages, b_stages;
   int tpb;             // taps per B stage (9, 3 or 1): one barrier round-trip per tpb taps
   uint32_t b_ring_off;
-  int BN, acc_cols, acc_stages, Cout;
+  int BN, acc_cols, acc_stages, Cout, tmem_cols;
   // output
   __nv_bfloat16* out;
   int out_mode, cy, o_coff;
@@ -217,9 +217,14 @@ __device__ __forceinline__ void flat_issue_chunk(const FlatParams& p, const uint
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// EW = number of epilogue warps.  EW = 8: one CTA per SM (all of shared memory, 2-deep activation ring,
+// each CTA walks 2 tiles).  EW = 4: half the shared memory, registers and TMEM per CTA so that TWO CTAs
+// are co-resident per SM -- one CTA's prologue, operand-load latency and epilogue then overlap the other
+// CTA's MMAs, and with programmatic dependent launch the next conv's CTAs are already resident and set
+// up while this conv drains.
+template <int EW>
+__global__ void __launch_bounds__(96 + 32 * EW, EW == 4 ? 2 : 1)
 conv_flat_kernel(const __grid_constant__ FlatParams p) {
-  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -241,8 +246,8 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
     }
     mbar_init(&tfull_bar[0], 2);
     mbar_init(&tfull_bar[1], 2);
-    mbar_init(&tempty_bar[0], 8);
-    mbar_init(&tempty_bar[1], 8);
+    mbar_init(&tempty_bar[0], EW);
+    mbar_init(&tempty_bar[1], EW);
     mbar_fence_init();
   }
   if (warp == 0 && lane == 0) {
@@ -251,13 +256,17 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
     tma_prefetch_desc(&p.w_map);
   }
   if (warp == 1) {
-    tmem_alloc(&tmem_base_s, 512);
+    tmem_alloc(&tmem_base_s, p.tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  // Dependents may be scheduled from here on: this CTA already owns its TMEM columns, so a co-resident
+  // CTA of the next kernel can never make it wait for an allocation (which would deadlock, because that
+  // CTA in turn waits for this grid to complete).
+  pdl_trigger();
   pdl_wait();   // everything above overlapped the previous kernel's tail
   if (warp == 0) DBG_T(1);
 
@@ -359,49 +368,54 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 3..10)
+    // ------------------------------------------------------------ epilogue (warps 3..3+EW-1)
+    // EW = 8: warps 3..6 -> rows [0,128), warps 7..10 -> rows [128,256); EW = 4: each warp does both halves.
     const int quad = warp & 3;            // TMEM lane quadrant accessible by this warp
-    const int half = (warp - 3) >> 2;     // warps 3..6 -> rows [0,128), warps 7..10 -> rows [128,256)
+    constexpr int NH = (EW == 8) ? 1 : 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       if (p.dbg_flags & 4) break;
-      const long long m = (long long)tile * kTileM + half * 128 + quad * 32 + lane;
-      const int nimg = (int)(m / p.HpWp);
-      const int rem = (int)(m - (long long)nimg * p.HpWp);
-      const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
-      const bool valid = (m < p.P) && yp >= 1 && yp <= p.h && xp >= 1 && xp <= p.w;
-      __nv_bfloat16* out_px;
-      long long up_sx = 0, up_sy = 0;
-      if (p.out_mode == 0) {
-        out_px = p.out + m * p.cy;
-      } else if (p.out_mode == 1) {
-        out_px = p.out + (((long long)nimg * p.h + (yp - 1)) * p.w + (xp - 1)) * p.cy;
-      } else {
-        up_sx = p.cy;
-        up_sy = (long long)2 * p.w * p.cy;
-        out_px = p.out + (((long long)nimg * 2 * p.h + 2 * (yp - 1)) * 2 * p.w + 2 * (xp - 1)) * p.cy;
-      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (warp == 3) DBG_T(tile == (int)blockIdx.x ? 5 : 7);
-      const uint32_t t_row = tmem + ((uint32_t)(quad * 32) << 16) + acc * 2 * p.acc_cols + half * p.acc_cols;
-      int c0 = 0;
-      for (; c0 + 32 <= p.BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_row + c0, r);
-        EpiLoads<32> L;
-        if (valid) flat_epilogue_load<32>(p, L, c0, m, out_px);
-        tmem_ld_wait();
-        if (valid) flat_epilogue<32>(p, r, L, c0, out_px, up_sx, up_sy);
-      }
-      if (c0 < p.BN) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(t_row + c0, r);
-        EpiLoads<16> L;
-        if (valid) flat_epilogue_load<16>(p, L, c0, m, out_px);
-        tmem_ld_wait();
-        if (valid) flat_epilogue<16>(p, r, L, c0, out_px, up_sx, up_sy);
+#pragma unroll 1
+      for (int hh = 0; hh < NH; ++hh) {
+        const int half = (EW == 8) ? ((warp - 3) >> 2) : hh;
+        const long long m = (long long)tile * kTileM + half * 128 + quad * 32 + lane;
+        const int nimg = (int)(m / p.HpWp);
+        const int rem = (int)(m - (long long)nimg * p.HpWp);
+        const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
+        const bool valid = (m < p.P) && yp >= 1 && yp <= p.h && xp >= 1 && xp <= p.w;
+        __nv_bfloat16* out_px;
+        long long up_sx = 0, up_sy = 0;
+        if (p.out_mode == 0) {
+          out_px = p.out + m * p.cy;
+        } else if (p.out_mode == 1) {
+          out_px = p.out + (((long long)nimg * p.h + (yp - 1)) * p.w + (xp - 1)) * p.cy;
+        } else {
+          up_sx = p.cy;
+          up_sy = (long long)2 * p.w * p.cy;
+          out_px = p.out + (((long long)nimg * 2 * p.h + 2 * (yp - 1)) * 2 * p.w + 2 * (xp - 1)) * p.cy;
+        }
+        const uint32_t t_row = tmem + ((uint32_t)(quad * 32) << 16) + acc * 2 * p.acc_cols + half * p.acc_cols;
+        int c0 = 0;
+        for (; c0 + 32 <= p.BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + c0, r);
+          EpiLoads<32> L;
+          if (valid) flat_epilogue_load<32>(p, L, c0, m, out_px);
+          tmem_ld_wait();
+          if (valid) flat_epilogue<32>(p, r, L, c0, out_px, up_sx, up_sy);
+        }
+        if (c0 < p.BN) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(t_row + c0, r);
+          EpiLoads<16> L;
+          if (valid) flat_epilogue_load<16>(p, L, c0, m, out_px);
+          tmem_ld_wait();
+          if (valid) flat_epilogue<16>(p, r, L, c0, out_px, up_sx, up_sy);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -418,7 +432,7 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
   tc_fence_before();
   __syncthreads();
   if (warp == 0) DBG_T(9);
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == 1) tmem_dealloc(tmem, p.tmem_cols);
 }
 
 // ---------------------------------------------------------------- layout helpers
@@ -491,10 +505,18 @@ extern "C" int b200_conv3x3_flat(const b200_flat_desc* d, const void* x, const v
   B200_REQUIRE(d->cx % 8 == 0 && d->cy % 8 == 0 && d->cin_off % 8 == 0 && d->cout_off % 8 == 0,
                "b200_conv3x3_flat: channel pitches/offsets must be multiples of 8");
   static bool attr_set = false;
+  static int two_cta = 0;   // measured slower at ~1.85 tiles per SM (both CTAs run in lockstep); opt-in via B200_FLAT_2CTA=1
   const int kSmemBytes = 200 * 1024;
+  const int kSmemBytes2 = 112 * 1024;   // two co-resident CTAs per SM (228 KB - 1 KB reserved per CTA)
   if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_flat_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kSmemBytes));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_flat_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kSmemBytes2));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_flat_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
+    const char* e = getenv("B200_FLAT_2CTA");
+    if (e) two_cta = atoi(e);
     attr_set = true;
   }
   FlatParams p;
@@ -536,17 +558,40 @@ extern "C" int b200_conv3x3_flat(const b200_flat_desc* d, const void* x, const v
   // taps per B stage: fewer barrier round trips for the MMA issuers when the weight tiles are small
   p.tpb = (9 * p.b_tap_bytes <= 40 * 1024) ? 9 : ((3 * p.b_tap_bytes <= 50 * 1024) ? 3 : 1);
   p.b_stage_bytes = p.b_tap_bytes * p.tpb;
-  const int budget = kSmemBytes - 2048;
-  p.a_stages = 2;
-  p.b_stages = (budget - p.a_stages * (int)p.a_stage_bytes) / (int)p.b_stage_bytes;
-  if (p.b_stages > kMaxBStages) p.b_stages = kMaxBStages;
-  while (p.a_stages < 3 && p.b_stages >= 3 &&
-         budget - (p.a_stages + 1) * (int)p.a_stage_bytes >= 3 * (int)p.b_stage_bytes) {
-    ++p.a_stages;
+  p.tmem_cols = 512;
+  bool use2 = false;
+  if (two_cta && 2 * p.acc_cols * p.acc_stages <= 256) {
+    // half-SM configuration: one activation stage, >= 2 weight stages of as many taps as fit
+    const int budget2 = kSmemBytes2 - 2048 - (int)p.a_stage_bytes;
+    for (int tpb : {9, 3, 1}) {
+      const int st = (int)p.b_tap_bytes * tpb;
+      if (budget2 >= 2 * st) {
+        use2 = true;
+        p.tpb = tpb;
+        p.b_stage_bytes = (uint32_t)st;
+        p.a_stages = 1;
+        p.b_stages = budget2 / st;
+        if (p.b_stages > kMaxBStages) p.b_stages = kMaxBStages;
+        int need = 2 * p.acc_cols * p.acc_stages;
+        p.tmem_cols = 32;
+        while (p.tmem_cols < need) p.tmem_cols *= 2;
+        break;
+      }
+    }
+  }
+  if (!use2) {
+    const int budget = kSmemBytes - 2048;
+    p.a_stages = 2;
     p.b_stages = (budget - p.a_stages * (int)p.a_stage_bytes) / (int)p.b_stage_bytes;
     if (p.b_stages > kMaxBStages) p.b_stages = kMaxBStages;
+    while (p.a_stages < 3 && p.b_stages >= 3 &&
+           budget - (p.a_stages + 1) * (int)p.a_stage_bytes >= 3 * (int)p.b_stage_bytes) {
+      ++p.a_stages;
+      p.b_stages = (budget - p.a_stages * (int)p.a_stage_bytes) / (int)p.b_stage_bytes;
+      if (p.b_stages > kMaxBStages) p.b_stages = kMaxBStages;
+    }
+    B200_REQUIRE(p.b_stages >= 2, "b200_conv3x3_flat: image too wide for the shared-memory A region (w=%d)", d->w);
   }
-  B200_REQUIRE(p.b_stages >= 2, "b200_conv3x3_flat: image too wide for the shared-memory A region (w=%d)", d->w);
   p.b_ring_off = (uint32_t)p.a_stages * p.a_stage_bytes;
   if (d->cin > 0) {
     uint64_t dims[2] = {(uint64_t)(d->cin_off + d->cin), (uint64_t)P};
@@ -595,9 +640,14 @@ extern "C" int b200_conv3x3_flat(const b200_flat_desc* d, const void* x, const v
     p.dbg_flags = f ? atoi(f) : 0;
   }
   const int sms = sm_count();
-  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024;
-  ::b200::launch_kernel(conv_flat_kernel, grid, kThreads, smem, as_stream(stream), p);
+  if (use2) {
+    const int grid = p.total_tiles < 2 * sms ? p.total_tiles : 2 * sms;
+    ::b200::launch_kernel(conv_flat_kernel<4>, grid, 96 + 32 * 4, smem, as_stream(stream), p);
+  } else {
+    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    ::b200::launch_kernel(conv_flat_kernel<8>, grid, kThreads, smem, as_stream(stream), p);
+  }
   B200_LAUNCH_CHECK();
   return 0;
 }

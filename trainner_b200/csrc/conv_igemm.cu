@@ -160,7 +160,6 @@ __device__ __forceinline__ void epilogue_columns(const IgemmParams& p, const uin
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
-  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -193,6 +192,10 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  // Dependents may be scheduled from here on: this CTA already owns its TMEM columns, so a co-resident
+  // CTA of the next kernel can never make it wait for an allocation (which would deadlock, because that
+  // CTA in turn waits for this grid to complete).
+  pdl_trigger();
   pdl_wait();   // everything above overlapped the previous kernel's tail
   const int k_iters = p.ntaps * p.k_chunks;
 
@@ -404,7 +407,6 @@ __device__ __forceinline__ void epi256_store(const IgemmParams& p, const uint32_
 
 __global__ void __launch_bounds__(kThreads256, 1)
 conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
-  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -436,6 +438,10 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  // Dependents may be scheduled from here on: this CTA already owns its TMEM columns, so a co-resident
+  // CTA of the next kernel can never make it wait for an allocation (which would deadlock, because that
+  // CTA in turn waits for this grid to complete).
+  pdl_trigger();
   pdl_wait();   // everything above overlapped the previous kernel's tail
   const int k_iters = p.ntaps * p.k_chunks;
 

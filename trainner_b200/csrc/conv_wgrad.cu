@@ -35,7 +35,6 @@ struct WgradParams {
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
-  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -63,6 +62,10 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  // Dependents may be scheduled from here on: this CTA already owns its TMEM columns, so a co-resident
+  // CTA of the next kernel can never make it wait for an allocation (which would deadlock, because that
+  // CTA in turn waits for this grid to complete).
+  pdl_trigger();
   pdl_wait();   // everything above overlapped the previous kernel's tail
   const int acc_cols = (p.BN + 31) & ~31;
 

@@ -18,6 +18,8 @@
 // element is owned by exactly one item), then `+=` into the fp32 OIHW gradient tensors.
 //
 // Reference: autograd wgrad of the 5 convs of ResidualDenseBlock_5C (RRDBNet_arch.py:130-148).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -36,19 +38,25 @@ struct RdbItemParams {
   const b200_wgrad_rdb_entry* rdbs;  // device table
   int n_rdb, P, Wp, k_steps, total_items;
   int nf, gc;
+  int k_split, k_per;   // positions are split into k_split slices of k_per k-steps (see the host entry)
 };
 
-__device__ __forceinline__ void item_decode(int item, int& r, int& dy, int& type) {
-  // heaviest type first so that the static round-robin schedule balances
+__device__ __forceinline__ void item_decode(const RdbItemParams& p, int item, int& r, int& dy, int& type,
+                                            int& ks0, int& ks1) {
+  // heaviest type first so that the static round-robin schedule balances; the 9 * k_split items of one
+  // RDB are adjacent so that the CTAs running at any moment share the same two or three RDBs' tensors
   type = item % 3;
   int q = item / 3;
   dy = q % 3 - 1;
-  r = q / 3;
+  q /= 3;
+  const int slice = q % p.k_split;
+  r = q / p.k_split;
+  ks0 = slice * p.k_per;
+  ks1 = ks0 + p.k_per < p.k_steps ? ks0 + p.k_per : p.k_steps;
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_rdb_kernel(const __grid_constant__ RdbItemParams p) {
-  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -74,6 +82,10 @@ wgrad_rdb_kernel(const __grid_constant__ RdbItemParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  // Dependents may be scheduled from here on: this CTA already owns its TMEM columns, so a co-resident
+  // CTA of the next kernel can never make it wait for an allocation (which would deadlock, because that
+  // CTA in turn waits for this grid to complete).
+  pdl_trigger();
   pdl_wait();   // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
@@ -81,12 +93,12 @@ wgrad_rdb_kernel(const __grid_constant__ RdbItemParams p) {
     int stage = 0;
     uint32_t phase = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      int r, dy, type;
-      item_decode(item, r, dy, type);
+      int r, dy, type, ks0, ks1;
+      item_decode(p, item, r, dy, type, ks0, ks1);
       const CUtensorMap* xm = p.maps + 3 * r;
       const CUtensorMap* gm = xm + 1;
       const CUtensorMap* om = xm + 2;
-      for (int ks = 0; ks < p.k_steps; ++ks) {
+      for (int ks = ks0; ks < ks1; ++ks) {
         const int m0 = ks * 128;
         const int xr = m0 + dy * p.Wp - 1;
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -123,13 +135,13 @@ wgrad_rdb_kernel(const __grid_constant__ RdbItemParams p) {
     int stage = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      int r, dy, type;
-      item_decode(item, r, dy, type);
+      int r, dy, type, ks0, ks1;
+      item_decode(p, item, r, dy, type, ks0, ks1);
       const int N = (type == 0) ? 128 : 64;
       const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
       mbar_wait(&tempty_bar, acc_phase ^ 1);
       tc_fence_after();
-      for (int ks = 0; ks < p.k_steps; ++ks) {
+      for (int ks = ks0; ks < ks1; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t s0 = smem_base + stage * kStageBytes;
@@ -154,11 +166,11 @@ wgrad_rdb_kernel(const __grid_constant__ RdbItemParams p) {
               const uint32_t b_addr = b_base + (uint32_t)((b_shift ? t : 0) + k * 16) * 128;
               const uint64_t ad = a_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
               const uint64_t bd = b_hi | (uint64_t)((b_addr >> 4) & 0x3FFF);
-              umma_f16(tmem + t * N, ad, bd, idesc, (ks | k) != 0);
+              umma_f16(tmem + t * N, ad, bd, idesc, ks != ks0 || k != 0);
             }
           }
           umma_commit(&empty_bar[stage]);
-          if (ks == p.k_steps - 1) umma_commit(&tfull_bar);
+          if (ks == ks1 - 1) umma_commit(&tfull_bar);
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -175,8 +187,8 @@ wgrad_rdb_kernel(const __grid_constant__ RdbItemParams p) {
     uint32_t acc_phase = 0;
     const int nf = p.nf, gc = p.gc;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      int r, dy, type;
-      item_decode(item, r, dy, type);
+      int r, dy, type, ks0, ks1;
+      item_decode(p, item, r, dy, type, ks0, ks1);
       const b200_wgrad_rdb_entry e = p.rdbs[r];
       const int N = (type == 0) ? 128 : 64;
       mbar_wait(&tfull_bar, acc_phase);
@@ -212,7 +224,10 @@ wgrad_rdb_kernel(const __grid_constant__ RdbItemParams p) {
                 if (ci < cin4) dst = e.dw[3] + ((size_t)(row - gc) * cin4 + ci) * 9 + tap;
               }                              // dY3 -> conv3 has only 128 inputs: nothing here
             }
-            if (dst) *dst += scale * __uint_as_float(v[j]);
+            if (dst) {
+              if (p.k_split > 1) atomicAdd(dst, scale * __uint_as_float(v[j]));   // slices of one item race
+              else *dst += scale * __uint_as_float(v[j]);
+            }
           }
         }
       }
@@ -307,7 +322,21 @@ extern "C" int b200_wgrad_rdb(const void* maps_dev, const b200_wgrad_rdb_entry* 
   p.P = (int)P;
   p.Wp = w + 2;
   p.k_steps = (int)((P + 127) / 128);
-  p.total_items = n_rdb * 9;
+  // Split-K for L2 locality, not for parallelism: with one item per (rdb, kernel row, type) the 148 CTAs
+  // would stream 16 different RDBs (53 MB of X/dY each) at once and every operand byte would come from
+  // HBM (18.6 GB per launch at config 2).  With S slices the CTAs in flight cover 16/S RDBs; the price is
+  // an exposed epilogue of scattered fp32 atomics per slice (single TMEM accumulator).  Measured on B200,
+  // config 2: S=1 3.76 ms, S=4 3.41 ms, S=8 4.32 ms, S=16 6.08 ms (operand phase alone: 2.55 ms for S>=4).
+  static int ksplit_env = -1;
+  if (ksplit_env < 0) {
+    const char* e = getenv("B200_WGRAD_RDB_KSPLIT");
+    ksplit_env = e ? atoi(e) : 4;
+    if (ksplit_env < 1) ksplit_env = 1;
+  }
+  p.k_split = ksplit_env < p.k_steps ? ksplit_env : 1;
+  p.k_per = (p.k_steps + p.k_split - 1) / p.k_split;
+  p.k_split = (p.k_steps + p.k_per - 1) / p.k_per;   // no empty slices
+  p.total_items = n_rdb * 9 * p.k_split;
   p.nf = nf;
   p.gc = gc;
   const int sms = sm_count();
