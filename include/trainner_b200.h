@@ -256,6 +256,13 @@ int b200_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int32_t n, int3
  * read from mask_up[n,2y,2x,c] (the upsampled activation itself, [n,2h,2w,c]) when non-null.   */
 int b200_sumpool2x2_mask(const void* dy, const void* mask_up, void* dx, int32_t n, int32_t h,
                          int32_t w, int32_t c, float slope, b200_stream_t stream);
+/* nn.PixelShuffle(2) on NHWC bf16 (+ LeakyReLU when act != 0), pixelshuffle_block block.py:374-387:
+ * out[n, 2y+i, 2x+j, c'] = act(z[n, y, x, 4c' + 2i + j]);  z is [n,h,w,4c], out is [n,2h,2w,c].
+ * b200_pixel_unshuffle2 is its transpose (the input gradient): dz[n,y,x,4c'+2i+j] = dout[n,2y+i,2x+j,c']. */
+int b200_pixel_shuffle2(const void* z, void* out, int32_t n, int32_t h, int32_t w, int32_t c,
+                        int32_t act, float slope, b200_stream_t stream);
+int b200_pixel_unshuffle2(const void* dout, void* dz, int32_t n, int32_t h, int32_t w, int32_t c,
+                          b200_stream_t stream);
 /* dst[p, dst_coff + c] += src[p, src_coff + c] on NHWC bf16 slices                              */
 int b200_add_slice_bf16(void* dst, int32_t dst_c, int32_t dst_coff, const void* src, int32_t src_c,
                         int32_t src_coff, int64_t npix, int32_t c, b200_stream_t stream);

@@ -251,3 +251,19 @@ def test_conv_flat_rdb_semantics():
     got = nchw(ops.from_flat(g))
     assert rel(got[:, :96], refg[:, :96]) < 5e-3
     assert torch.equal(got[:, 96:], dbuf[:, 96:])
+
+
+def test_pixel_shuffle():
+    """nn.PixelShuffle(2) + LeakyReLU on NHWC bf16 and its transpose (pixelshuffle_block, block.py:374-387): bit-exact
+    data movement (bf16 in, bf16 out; the activation is exact in bf16 up to one rounding)."""
+    from trainner_b200 import ops
+    z = rnd(2, 64, 6, 10, seed=3)                       # NCHW, 4 * 16 channels
+    y = ops.pixel_shuffle2(nhwc(z), act=1, slope=0.2)
+    ref = F.leaky_relu(F.pixel_shuffle(z, 2), 0.2)
+    assert y.shape == (2, 12, 20, 16)
+    assert rel(nchw(y), ref) < 3e-3
+    y0 = ops.pixel_shuffle2(nhwc(z), act=0)
+    assert torch.equal(nchw(y0), F.pixel_shuffle(z, 2))
+    dy = rnd(2, 16, 12, 20, seed=4)
+    dz = ops.pixel_unshuffle2(nhwc(dy))
+    assert torch.equal(nchw(dz), F.pixel_unshuffle(dy, 2))

@@ -37,12 +37,13 @@ def seeded(shapes, seed, gain=None):
     return sd
 
 
-def test_rrdbnet_forward_backward_vs_oracle_and_golden():
+@pytest.mark.parametrize("mode", ["upconv", "pixelshuffle"])
+def test_rrdbnet_forward_backward_vs_oracle_and_golden(mode):
     from oracle import esrgan_oracle as O
     from trainner_b200.architectures import RRDBNet_arch
-    fx = torch.load(os.path.join(GOLD, "modules.pt"))["rrdb_upconv"]
+    fx = torch.load(os.path.join(GOLD, "modules.pt"))["rrdb_" + mode]
     sd = seeded(fx["shapes"], fx["seed"])
-    net = RRDBNet_arch.RRDBNet(3, 3, 64, 2).cuda()
+    net = RRDBNet_arch.RRDBNet(3, 3, 64, 2, upsample_mode=mode).cuda()
     net.load_state_dict(sd)
     x = fx["x"]
     y = net(x.cuda())
@@ -53,7 +54,7 @@ def test_rrdbnet_forward_backward_vs_oracle_and_golden():
     def oracle(autocast):
         p = OrderedDict((k, v.clone().cuda().requires_grad_(True)) for k, v in sd.items())
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
-            yo = O.rrdbnet_forward(p, x.cuda(), 2)
+            yo = O.rrdbnet_forward(p, x.cuda(), 2, mode)
         yo.float().backward(dy.cuda())
         return yo.detach().float(), OrderedDict((k, v.grad.float()) for k, v in p.items())
 
@@ -66,8 +67,11 @@ def test_rrdbnet_forward_backward_vs_oracle_and_golden():
         e, e_ref = rel(p.grad, g32[k]), rel(g16[k], g32[k])
         errs.append(e)
         errs_ref.append(e_ref)
-        if e > max(0.03, 1.5 * e_ref) or cos(p.grad, g32[k]) < 0.995:
-            bad.append((k, e, e_ref, cos(p.grad, g32[k])))
+        # direction: cos >= 0.995, or (where the reference's own bf16 path is further off than that, as in the
+        # pixelshuffle net whose seeded weights amplify rounding noise to ~11 %) no further than 1.5x its angle
+        c_min = min(0.995, 1.0 - 1.5 * (1.0 - cos(g16[k], g32[k])))
+        if e > max(0.03, 1.5 * e_ref) or cos(p.grad, g32[k]) < c_min:
+            bad.append((k, e, e_ref, cos(p.grad, g32[k]), c_min))
     assert not bad, bad[:10]
     # aggregate: no worse than the reference's own bf16 path
     assert sum(errs) / len(errs) <= 1.1 * sum(errs_ref) / len(errs_ref)

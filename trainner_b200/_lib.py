@@ -133,6 +133,8 @@ _SIGNATURES = {
     "b200_maxpool2x2": [_P, _P, _I, _I, _I, _I, _P],
     "b200_maxpool2x2_bwd": [_P, _P, _P, _I, _I, _I, _I, _P],
     "b200_sumpool2x2_mask": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "b200_pixel_shuffle2": [_P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "b200_pixel_unshuffle2": [_P, _P, _I, _I, _I, _I, _P],
     "b200_add_slice_bf16": [_P, _I, _I, _P, _I, _I, _L, _I, _P],
     "b200_l1_loss_f32": [_P, _P, _P, _P, _L, _F, _P],
     "b200_l1_loss_bf16": [_P, _P, _P, _P, _L, _F, _P],

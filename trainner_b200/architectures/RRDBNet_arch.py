@@ -133,9 +133,6 @@ class RRDBNet(nn.Module):
                 "hr1": convs[-1]}
 
     def forward(self, x, outm=None):
-        if self.upsample_mode != "upconv":
-            raise NotImplementedError("B200 RRDBNet forward: only upsample_mode='upconv' is implemented "
-                                      "(pixelshuffle keeps its state_dict layout; kernel pending)")
         if self.gaussian_noise and self.training:
             raise NotImplementedError("network_G.gaussian (ESRGAN+ noise, block.py:587) is not on the B200 "
                                       "path; set gaussian: false (SURVEY.md 8c)")

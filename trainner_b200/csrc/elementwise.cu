@@ -210,6 +210,54 @@ __global__ void add_small_kernel(float* __restrict__ dst, const float* __restric
   if (i < n) dst[i] += src[i];
 }
 
+// ------------------------------------------------------------------ PixelShuffle(2) (block.py:383)
+// out[n, 2y+i, 2x+j, c] = act(z[n, y, x, 4c + 2i + j]).  One thread moves 32 input channels (8 output
+// channels for each of the 4 sub-pixels): four 16-byte loads, four 16-byte stores.
+template <int BWD>
+__global__ void pixel_shuffle2_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                      int n, int h, int w, int c, int act, float slope) {
+  pdl_trigger();
+  pdl_wait();
+  const int qn = c / 8;
+  const long long total = (long long)n * h * w * qn;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(idx % qn);
+    long long r = idx / qn;
+    const int x = (int)(r % w);
+    r /= w;
+    const int y = (int)(r % h);
+    const int b = (int)(r / h);
+    const long long zoff = ((((long long)b * h + y) * w + x) * 4 * c) + 32 * q;          // [.., 4c] pixel
+    float v[32];
+    if (BWD == 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) unpack8(*reinterpret_cast<const uint4*>(src + zoff + 8 * u), v + 8 * u);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long ooff = ((((long long)b * 2 * h + 2 * y + (k >> 1)) * 2 * w + 2 * x + (k & 1)) * c) + 8 * q;
+      float o[8];
+      if (BWD == 0) {
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+          const float t = v[cc * 4 + k];
+          o[cc] = (act && t < 0.f) ? t * slope : t;
+        }
+        *reinterpret_cast<uint4*>(dst + ooff) = pack8(o);
+      } else {
+        unpack8(*reinterpret_cast<const uint4*>(src + ooff), o);
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) v[cc * 4 + k] = o[cc];
+      }
+    }
+    if (BWD == 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(dst + zoff + 8 * u) = pack8(v + 8 * u);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ MaxPool 2x2
 __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                int n, int h, int w, int c) {
@@ -534,6 +582,26 @@ int b200_sumpool2x2_mask(const void* dy, const void* mask, void* dx, int32_t n, 
   const long long total = (long long)n * h * w * (c / 8);
   ::b200::launch_kernel(sumpool_mask_kernel, grid_for(total, 256), 256, 0, as_stream(stream), 
       (const bf16*)dy, (const bf16*)mask, (bf16*)dx, n, h, w, c, slope);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200_pixel_shuffle2(const void* z, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t act,
+                        float slope, b200_stream_t stream) {
+  B200_REQUIRE(z && out && c % 8 == 0, "b200_pixel_shuffle2: c (output channels) must be a multiple of 8");
+  const long long total = (long long)n * h * w * (c / 8);
+  ::b200::launch_kernel(pixel_shuffle2_kernel<0>, grid_for(total, 256), 256, 0, as_stream(stream),
+                        (const bf16*)z, (bf16*)out, n, h, w, c, act, slope);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200_pixel_unshuffle2(const void* dout, void* dz, int32_t n, int32_t h, int32_t w, int32_t c,
+                          b200_stream_t stream) {
+  B200_REQUIRE(dout && dz && c % 8 == 0, "b200_pixel_unshuffle2: c (output channels) must be a multiple of 8");
+  const long long total = (long long)n * h * w * (c / 8);
+  ::b200::launch_kernel(pixel_shuffle2_kernel<1>, grid_for(total, 256), 256, 0, as_stream(stream),
+                        (const bf16*)dout, (bf16*)dz, n, h, w, c, 0, 0.f);
   B200_LAUNCH_CHECK();
   return 0;
 }

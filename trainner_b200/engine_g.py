@@ -144,12 +144,19 @@ class RRDBNetEngine:
         ctx.B = [z(N, h + 2, w + 2, C) for _ in range(nrdb)] + [z(N, h + 2, w + 2, nf)]   # flat, zero border
         Bc = [C] * nrdb + [nf]
         ctx.F0 = e(N, h, w, nf)
-        # upsampler chain: U[i] is the (already nearest-upsampled) input of upconv i
-        ctx.U = []
+        # upsampler chain.  upconv: U[i] is the (already nearest-upsampled) input of upconv i.
+        # pixelshuffle (block.py:374-387): U[i] is the input of conv i at ITS resolution and Z[i] the
+        # 4*nf-channel pre-shuffle conv output.
+        self.shuffle = (net.upsample_mode == "pixelshuffle")
+        ctx.U, ctx.Z = [], []
         hh, ww = h, w
         for _ in self.ups:
+            if self.shuffle:
+                ctx.U.append(e(N, hh, ww, nf))
+                ctx.Z.append(e(N, hh, ww, 4 * nf))
             hh, ww = hh * 2, ww * 2
-            ctx.U.append(e(N, hh, ww, nf))
+            if not self.shuffle:
+                ctx.U.append(e(N, hh, ww, nf))
         H, W = hh, ww
         ctx.V = e(N, H, W, nf)    # output of the last upconv (or of LR_conv when there is none)
         ctx.Wt = e(N, H, W, nf)   # output of HR_conv0
@@ -208,10 +215,20 @@ class RRDBNetEngine:
         L = self.lr
         first_dst = ctx.U[0] if self.ups else ctx.V
         d = make_flat_desc(N, h, w, nf, 0, nf, nf, 0, nf, taps_conv(3, 1), L.taps, L.fwd_rows, L.fwd_cols,
-                           out_mode=2 if self.ups else 1, beta1=1.0, res_nch=nf, res1_c=Bc[0], res1_coff=0)
+                           out_mode=2 if (self.ups and not self.shuffle) else 1, beta1=1.0, res_nch=nf,
+                           res1_c=Bc[0], res1_coff=0)
         add_flat(f, d, ctx.B[nrdb], L.w_fwd, L.bias, res1=ctx.B[0], y=first_dst)
         hh, ww = h, w
-        for i, L in enumerate(self.ups):
+        for i, L in enumerate(self.ups if self.shuffle else []):
+            # conv nf -> 4 nf at (hh, ww), then PixelShuffle(2) + LeakyReLU into the next stage's input
+            lastu = (i == len(self.ups) - 1)
+            d = make_conv_desc(N, hh, ww, nf, 0, nf, hh, ww, hh, ww, 4 * nf, 0, 4 * nf, taps_conv(3, 1), L.taps,
+                               L.fwd_rows, L.fwd_cols)
+            add_igemm(f, d, ctx.U[i], L.w_fwd, L.bias, y=ctx.Z[i])
+            f.add(lib.b200_pixel_shuffle2, P(ctx.Z[i]), P(ctx.V if lastu else ctx.U[i + 1]), N, hh, ww, nf, 1,
+                  LRELU_SLOPE)
+            hh, ww = hh * 2, ww * 2
+        for i, L in enumerate([] if self.shuffle else self.ups):
             hh, ww = hh * 2, ww * 2
             lastu = (i == len(self.ups) - 1)
             dst = ctx.V if lastu else ctx.U[i + 1]
@@ -243,7 +260,8 @@ class RRDBNetEngine:
         ctx.dWt = e(N, H, W, nf)
         ctx.dV = e(N, H, W, nf)
         ctx.dU = [e(*u.shape) for u in ctx.U]
-        ctx.dP = [e(u.shape[0], u.shape[1] // 2, u.shape[2] // 2, nf) for u in ctx.U]
+        ctx.dP = [] if self.shuffle else [e(u.shape[0], u.shape[1] // 2, u.shape[2] // 2, nf) for u in ctx.U]
+        ctx.dZ = [e(*z_.shape) for z_ in ctx.Z]
         # one flat gradient buffer per RDB (kept until the batched weight-gradient kernel has run:
         # 70 x 27 MB at config 2 -- HBM is 180 GB, launch count and atomics are the scarce resource)
         ctx.G = [torch.zeros(N, h + 2, w + 2, CC, dtype=BF16, device=dev) for _ in range(nrdb + 1)]
@@ -265,7 +283,24 @@ class RRDBNetEngine:
         # upconvs, last to first.  dcur = gradient wrt the pre-activation of upconv i's conv output
         dcur = ctx.dV
         hh, ww = H, W
-        for i in range(len(self.ups) - 1, -1, -1):
+        for i in range(len(self.ups) - 1, -1, -1) if self.shuffle else []:
+            # dcur = gradient wrt shuffle(Z[i]) (the LeakyReLU mask was applied by the consumer's dgrad)
+            L = self.ups[i]
+            hh, ww = hh // 2, ww // 2
+            b.add(lib.b200_pixel_unshuffle2, P(dcur), P(ctx.dZ[i]), N, hh, ww, nf)
+            add_wgrad(b, N, hh, ww, nf, 0, nf, hh, ww, 4 * nf, 0, 4 * nf, 3, 1, 1, 1.0, ctx.U[i], ctx.dZ[i],
+                      g(L.weight), g(L.bias))
+            if i > 0:   # U[i] = lrelu(shuffle(Z[i-1])) carries the mask of the previous stage
+                d = make_conv_desc(N, hh, ww, 4 * nf, 0, 4 * nf, hh, ww, hh, ww, nf, 0, nf, taps_dgrad_s1(3, 1),
+                                   L.taps, L.dgr_rows, L.dgr_cols, mask_c=nf, mask_coff=0, mask_lo=0, mask_hi=nf,
+                                   mask_slope=SL)
+                add_igemm(b, d, ctx.dZ[i], L.w_dgr, mask=ctx.U[i], y=ctx.dU[i])
+            else:
+                d = make_conv_desc(N, hh, ww, 4 * nf, 0, 4 * nf, hh, ww, hh, ww, nf, 0, nf, taps_dgrad_s1(3, 1),
+                                   L.taps, L.dgr_rows, L.dgr_cols)
+                add_igemm(b, d, ctx.dZ[i], L.w_dgr, y=ctx.dU[i])
+            dcur = ctx.dU[i]
+        for i in range(len(self.ups) - 1, -1, -1) if not self.shuffle else []:
             L = self.ups[i]
             d = make_conv_desc(N, hh, ww, nf, 0, nf, hh, ww, hh, ww, nf, 0, nf, taps_dgrad_s1(3, 1), L.taps,
                                L.dgr_rows, L.dgr_cols)

@@ -189,6 +189,25 @@ def maxpool2x2(x):
     return y
 
 
+def pixel_shuffle2(z, act=0, slope=0.2):
+    """nn.PixelShuffle(2) (+ LeakyReLU) on NHWC bf16: [N,h,w,4c] -> [N,2h,2w,c] (block.py:383)."""
+    require_device(z, "pixel_shuffle2")
+    N, H, W, C4 = z.shape
+    y = torch.empty(N, 2 * H, 2 * W, C4 // 4, dtype=BF16, device=z.device)
+    _lib.check(lib.b200_pixel_shuffle2(_p(z), _p(y), N, H, W, C4 // 4, int(act), float(slope), stream_ptr()),
+               "pixel_shuffle2")
+    return y
+
+
+def pixel_unshuffle2(dy):
+    """Input gradient of pixel_shuffle2: [N,2h,2w,c] -> [N,h,w,4c]."""
+    require_device(dy, "pixel_unshuffle2")
+    N, H2, W2, Cc = dy.shape
+    dz = torch.empty(N, H2 // 2, W2 // 2, 4 * Cc, dtype=BF16, device=dy.device)
+    _lib.check(lib.b200_pixel_unshuffle2(_p(dy), _p(dz), N, H2 // 2, W2 // 2, Cc, stream_ptr()), "pixel_unshuffle2")
+    return dz
+
+
 def maxpool2x2_backward(x, dy):
     require_device(x, "maxpool2x2_backward")
     N, H, W, Cc = x.shape
