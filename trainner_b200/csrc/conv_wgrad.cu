@@ -10,6 +10,7 @@
 //
 // Reference call site: autograd backward of nn.Conv2d, block.py:238 (aten::convolution_backward).
 #include "common.cuh"
+#include "colsum.cuh"
 #include "sm100_ptx.cuh"
 
 namespace b200 {
@@ -192,28 +193,12 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
 }
 
 // Per-channel column sum of an NHWC bf16 slice: db[c] += scale * sum_p dy[p, coff + c]
-__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
-                              long long npix, int cdy, int coff, int c, float scale) {
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
+                                                     long long npix, int cdy, int coff, int c, float scale) {
   pdl_trigger();
   pdl_wait();
-  // block: 256 threads = 8 pixel lanes x 32 channel lanes; grid.y over channel groups of 32
-  const int cl = threadIdx.x & 31;
-  const int pl = threadIdx.x >> 5;
-  const int ch = blockIdx.y * 32 + cl;
-  float s = 0.f;
-  if (ch < c) {
-    for (long long pix = (long long)blockIdx.x * 8 + pl; pix < npix; pix += (long long)gridDim.x * 8)
-      s += __bfloat162float(dy[pix * cdy + coff + ch]);
-  }
-  __shared__ float red[8][33];
-  red[pl][cl] = s;
-  __syncthreads();
-  if (pl == 0 && ch < c) {
-    float tot = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) tot += red[i][cl];
-    atomicAdd(db + ch, scale * tot);
-  }
+  __shared__ float red[256 * 8];
+  colsum_vec(dy, npix, cdy, coff, c, scale, db, red);
 }
 
 // One thread converts all taps of one (row, col) weight: the fp32 source is read as `taps` consecutive
@@ -286,8 +271,13 @@ extern "C" int b200_conv_wgrad(const b200_wgrad_desc* d, const void* x, const vo
                "b200_conv_wgrad: channel pitches/offsets must be multiples of 8");
   const long long npix = (long long)d->n * d->h_out * d->w_out;
   if (dbias) {
-    dim3 grid((unsigned)((npix + 8 * 64 - 1) / (8 * 64) < 1024 ? (npix + 8 * 64 - 1) / (8 * 64) : 1024),
-              (d->cout + 31) / 32);
+    B200_REQUIRE(d->cout % 8 == 0 && d->cout <= 2048, "b200_conv_wgrad: bias gradient needs cout %% 8 == 0, <= 2048");
+    // one block covers (256 / (cout/8)) pixel lanes x 4 pixels in flight; at most 4 waves of blocks
+    const long long per_block = (long long)(256 / (d->cout / 8)) * 16;
+    long long gx = (npix + per_block - 1) / per_block;
+    if (gx > 148 * 4) gx = 148 * 4;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, 1);
     ::b200::launch_kernel(colsum_kernel, grid, 256, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(dy),
                                                       dbias, npix, d->cdy, d->dy_coff, d->cout,
                                                       d->scale);

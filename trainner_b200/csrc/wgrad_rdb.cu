@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "colsum.cuh"
 #include "sm100_ptx.cuh"
 
 namespace b200 {
@@ -242,30 +243,12 @@ wgrad_rdb_kernel(const __grid_constant__ RdbItemParams p) {
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-__global__ void colsum_multi_kernel(const b200_colsum_entry* __restrict__ table) {
+__global__ void __launch_bounds__(256) colsum_multi_kernel(const b200_colsum_entry* __restrict__ table) {
   pdl_trigger();
   pdl_wait();
+  __shared__ float red[256 * 8];
   const b200_colsum_entry e = table[blockIdx.y];
-  const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(e.src);
-  // 256 threads = 8 pixel lanes x 32 channel lanes; channel groups of 32 looped
-  const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
-  __shared__ float red[8][33];
-  for (int cg = 0; cg < e.c; cg += 32) {
-    const int ch = cg + cl;
-    float s = 0.f;
-    if (ch < e.c)
-      for (long long pix = (long long)blockIdx.x * 8 + pl; pix < e.npix; pix += (long long)gridDim.x * 8)
-        s += __bfloat162float(src[pix * e.pitch + e.coff + ch]);
-    __syncthreads();
-    red[pl][cl] = s;
-    __syncthreads();
-    if (pl == 0 && ch < e.c) {
-      float tot = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) tot += red[i][cl];
-      atomicAdd(e.dst + ch, e.scale * tot);
-    }
-  }
+  colsum_vec(reinterpret_cast<const __nv_bfloat16*>(e.src), e.npix, e.pitch, e.coff, e.c, e.scale, e.dst, red);
 }
 
 }  // namespace
@@ -276,6 +259,7 @@ using namespace b200;
 extern "C" int b200_colsum_multi(const b200_colsum_entry* table_dev, int32_t count, b200_stream_t stream) {
   if (count <= 0) return 0;
   B200_REQUIRE(table_dev, "b200_colsum_multi: null table");
+  // entries must have c % 8 == 0, c <= 2048, pitch % 8 == 0, coff % 8 == 0 (16-byte vector loads)
   dim3 grid(32, count);
   ::b200::launch_kernel(colsum_multi_kernel, grid, 256, 0, as_stream(stream), table_dev);
   B200_LAUNCH_CHECK();
@@ -327,6 +311,8 @@ extern "C" int b200_wgrad_rdb(const void* maps_dev, const b200_wgrad_rdb_entry* 
   // HBM (18.6 GB per launch at config 2).  With S slices the CTAs in flight cover 16/S RDBs; the price is
   // an exposed epilogue of scattered fp32 atomics per slice (single TMEM accumulator).  Measured on B200,
   // config 2: S=1 3.76 ms, S=4 3.41 ms, S=8 4.32 ms, S=16 6.08 ms (operand phase alone: 2.55 ms for S>=4).
+  // A tap-major fp32 scratch with warp-coalesced atomics + a finalize pass was tried and is SLOWER
+  // (S=8: 5.43 ms, S=16: 8.55 ms): 32 atomics of one line serialise in one L2 slice.
   static int ksplit_env = -1;
   if (ksplit_env < 0) {
     const char* e = getenv("B200_WGRAD_RDB_KSPLIT");
