@@ -76,9 +76,9 @@ def test_rrdbnet_forward_backward_vs_oracle_and_golden(mode):
     print("grad rel-err mean: cuda %.4f | reference bf16 %.4f (%s)" % (sum(errs) / len(errs),
                                                                     sum(errs_ref) / len(errs_ref), mode))
     assert not bad, (len(bad), bad[:10])
-    # aggregate: no worse than the reference's own bf16 path (upconv: measured better; pixelshuffle: the seeded
-    # 2-block net is ill-conditioned -- reference bf16 itself is 7-11 % off -- so allow 1.25x there)
-    assert sum(errs) / len(errs) <= (1.1 if mode == "upconv" else 1.25) * sum(errs_ref) / len(errs_ref)
+    # aggregate: no worse than the reference's own bf16 path (measured on B200: upconv 0.0568 vs 0.0608,
+    # pixelshuffle 0.0892 vs 0.0922 -- that seeded 2-block net is ill-conditioned, reference bf16 is 7-11 % off)
+    assert sum(errs) / len(errs) <= 1.1 * sum(errs_ref) / len(errs_ref)
 
 
 @pytest.mark.parametrize("size", [32, 64])
