@@ -227,6 +227,19 @@ def run_reference_cudnn(args):
                                  (args.nb, args.batch, args.hr)}}))
 
 
+def ncu_traffic_per_launch(tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
+    capture of one training step (profiles/r01_v5_conv_flat_dram_traffic.txt); None for other kernels."""
+    path = os.path.join(ROOT, "profiles", "r01_v5_conv_flat_dram_traffic.txt")
+    if tag != "conv_flat" or not os.path.exists(path):
+        return None, None
+    import re
+    m = re.search(r"DRAM read ([0-9.]+) MB, DRAM write ([0-9.]+) MB", open(path).read())
+    if not m:
+        return None, None
+    return (float(m.group(1)) + float(m.group(2))) * 1e6, "profiles/r01_v5_conv_flat_dram_traffic.txt"
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -269,9 +282,7 @@ def main():
         sink["log"] = model.get_current_log()     # device -> host read of the step's losses
 
     sampler = ClockSampler(local) if rank == 0 else None
-    l0 = _lib.launch_count()
     ms = timed_steps(step_resident, args.steps, args.warmup, world)
-    launches = int(round((_lib.launch_count() - l0) / float(args.steps + args.warmup) * args.steps))
     ms_e2e = timed_steps(step_e2e, args.steps, max(1, args.warmup // 2), world)
     clocks = sampler.stop() if sampler else None
 
@@ -294,11 +305,15 @@ def main():
         runtime.Plan.run = timed_run
         detail = [] if os.environ.get("B200_BENCH_DETAIL") else None
         runtime.Plan.detail_sink = detail
+        l0 = _lib.launch_count()
         try:
             step_resident()
         finally:
             runtime.Plan.run = orig_run
             runtime.Plan.detail_sink = None
+        # kernels of libtrainner_b200.so per step, counted at the C entry points during this eagerly executed
+        # step (the timed steps replay the same launches from CUDA graphs, which bypass the host-side counter)
+        launches = (_lib.launch_count() - l0) * args.steps
         if detail is not None and rank == 0:
             grp = {}
             for tag, info, t_ms, fl in detail:
@@ -319,8 +334,10 @@ def main():
         tag, (cnt, t_ms, fl) = dom
         achieved = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
         peak = pk["bf16_tflops_sustained"]
+        traffic, traffic_src = ncu_traffic_per_launch(tag)
         roof = {"bound": "tensor", "kernel": tag, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "launches_per_step": cnt,
+                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, mean)",
+                "traffic_source": traffic_src, "launches_per_step": cnt,
                 "avg_launch_ms": t_ms / cnt, "share_of_kernel_time": t_ms / total_ms if total_ms else None,
                 "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
                 "per_kernel": {k: {"launches": v[0], "ms": round(v[1], 3),

@@ -462,14 +462,14 @@ int main(int argc, char** argv) {
   if (argc > 1 && !strcmp(argv[1], "pipe")) {
     CK(cudaFuncSetAttribute(pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     for (int threads : {352})
-    for (int data : {0, 1})
+    for (int data : {1})
     for (int dstride : {128})
     for (int sep : {3})
     for (int commit_only : {1, 0})
       for (int N : {32, 64})
         for (int G : {4, 12, 36})
           for (int S : {2, 3, 4, 8}) {
-            if (S != 3 || G == 4 || commit_only) continue;
+            if (S != 3) continue;
             if (dstride < N) continue;
             PipeParams pp = {N, G, S, 1440 / G, 2, commit_only, sep, dstride, data};
             for (int it = 0; it < 2; ++it) {
