@@ -61,7 +61,6 @@ struct FlatParams {
   int mask_c, mask_coff, mask_lo, mask_hi;
   float mask_slope;
   long long* dbg;  // optional per-CTA timeline (clock64), 16 slots per CTA; nullptr in production
-  int dbg_flags;   // experiments only (wrong results): 1 = skip weight reloads, 2 = skip activation reloads
 };
 
 #define DBG_T(slot) do { if (p.dbg && lane == 0) p.dbg[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
@@ -278,9 +277,7 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
       const int row0 = tile * kTileM - p.halo;
       for (int c = 0; c < p.k_chunks; ++c) {
         mbar_wait(&a_empty[as], aph ^ 1);
-        if ((p.dbg_flags & 2) && (tile != (int)blockIdx.x || c >= p.a_stages)) {
-          if (elect_one()) mbar_arrive(&a_full[as]);
-        } else if (elect_one()) {
+        if (elect_one()) {
           uint8_t* sa = smem + (size_t)as * p.a_stage_bytes;
           mbar_expect_tx(&a_full[as], p.a_bytes);
           const CUtensorMap* im = (c < p.kc1) ? &p.in_map : &p.in2_map;
@@ -295,9 +292,7 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
         }
         for (int t0 = 0; t0 < 9; t0 += p.tpb) {
           mbar_wait(&b_empty[bs], bph ^ 1);
-          if ((p.dbg_flags & 1) && (tile != (int)blockIdx.x || c > 0)) {
-            if (elect_one()) mbar_arrive(&b_full[bs]);
-          } else if (elect_one()) {
+          if (elect_one()) {
             uint8_t* sb = smem + p.b_ring_off + (size_t)bs * p.b_stage_bytes;
             mbar_expect_tx(&b_full[bs], p.b_bytes * p.tpb);
             for (int j = 0; j < p.tpb; ++j)
@@ -375,7 +370,6 @@ conv_flat_kernel(const __grid_constant__ FlatParams p) {
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      if (p.dbg_flags & 4) break;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (warp == 3) DBG_T(tile == (int)blockIdx.x ? 5 : 7);
@@ -636,8 +630,6 @@ extern "C" int b200_conv3x3_flat(const b200_flat_desc* d, const void* x, const v
   {
     const char* e = getenv("B200_FLAT_DBG_PTR");
     p.dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
-    const char* f = getenv("B200_FLAT_DBG_FLAGS");
-    p.dbg_flags = f ? atoi(f) : 0;
   }
   const int sms = sm_count();
   const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024;
