@@ -81,6 +81,28 @@ def test_init_weights_class_name_contract():
     assert float(d.state_dict()["features.3.weight"].min()) == 1.0
 
 
+def test_init_weights_bit_identical_to_reference():
+    """same torch seed -> the tensors of the reference's init_weights (networks.py:71-100) on the
+    reference's own modules (tests/golden/make_golden_init.py), bit for bit: the module iteration order, the
+    class-name matching and every parameter shape are the reference's."""
+    from trainner_b200 import networks
+    from trainner_b200.architectures import RRDBNet_arch, discriminators
+    fx = torch.load(os.path.join(GOLD, "init.pt"))
+
+    def checks(sd):
+        return [(k, (float(v.double().sum()), float(v.double().abs().sum()))) for k, v in sd.items()]
+
+    for mode in ("upconv", "pixelshuffle"):
+        torch.manual_seed(1234)
+        g = RRDBNet_arch.RRDBNet(3, 3, 64, 2, upsample_mode=mode, gaussian_noise=False)
+        networks.init_weights(g, "kaiming", 0.1)
+        assert checks(g.state_dict()) == list(fx["G_%s" % mode].items()), mode
+    torch.manual_seed(4321)
+    d = discriminators.Discriminator_VGG(64, 3, 64)
+    networks.init_weights(d, "kaiming", 1)
+    assert checks(d.state_dict()) == list(fx["D_64"].items())
+
+
 def test_no_cpu_fallback():
     from trainner_b200.architectures import RRDBNet_arch
     from trainner_b200 import ops
