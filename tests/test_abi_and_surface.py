@@ -120,3 +120,21 @@ def test_product_code_never_imports_oracle():
             if f.endswith(".py") or f.endswith(".cu") or f.endswith(".cuh"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the reference's CPU algorithm = the oracle port, timed on host cores) prints ONE
+    JSON line with the keys the driver reads; tiny configuration so that it runs in seconds."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--nb", "1",
+                          "--hr", "32", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "hr_pixels_per_sec" and line["unit"] == "HR-px/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0 \
+        and line["e2e"]["d2h_bytes_per_step"] == 0
