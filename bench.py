@@ -12,7 +12,9 @@ Prints ONE JSON line (rank 0): value = HR-pixels/s over all GPUs with inputs res
 e2e = the same metric through the public API with pinned HOST batches (H2D inside the timed
 region, loss read back every step); roofline = tensor-pipe roofline of the dominant kernel
 (tcgen05 implicit-GEMM conv) from CUDA-event timings of every launch in one instrumented step;
-cpu_baseline = the reference algorithm (oracle port, fp32 PyTorch CPU) on this box's host cores.
+cpu_baseline = the unmodified reference SRModel (baseline/_ref) on this box's host cores (bounded sample);
+vs_cudnn = the unmodified reference SRModel on this GPU through PyTorch/cuDNN (bf16 autocast and native fp16 AMP).
+--impl reference / reference-cudnn run ONLY the reference (they never import trainner_b200 or oracle/).
 """
 import argparse
 import json
@@ -41,6 +43,7 @@ def parse():
     ap.add_argument("--nb", type=int, default=23)
     ap.add_argument("--hr", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cudnn-ref", action="store_true", help="skip the in-run reference-cuDNN rows (vs_cudnn)")
     return ap.parse_args()
 
 
@@ -146,84 +149,95 @@ def timed_steps(fn, steps, warmup, world):
     return ms / steps
 
 
-def cpu_reference_steps(args, steps, warmup, threads=None):
-    """The reference algorithm on host cores: oracle port (fp32 PyTorch CPU), batch 1 per step."""
-    from collections import OrderedDict
-    from oracle import esrgan_oracle as O
-    import torchvision
-    from trainner_b200 import networks
-    from trainner_b200.architectures import discriminators, RRDBNet_arch
+def reference_batch(args, batch, device=None, seed=1234):
+    gen = torch.Generator().manual_seed(seed)
+    lr_img = torch.rand(batch, 3, args.hr // 4, args.hr // 4, generator=gen)
+    hr_img = torch.rand(batch, 3, args.hr, args.hr, generator=gen)
+    if device is not None:
+        lr_img, hr_img = lr_img.to(device), hr_img.to(device)
+    return {"LR": lr_img, "HR": hr_img}
+
+
+def reference_model(args, gpu, precision, batch):
+    """The UNMODIFIED reference SRModel (baseline/_ref/codes/models/sr_model.py:17) built through the
+    reference's own create_model / networks / losses for BASELINE config 2."""
+    from baseline import reference_arm as RA
+    if gpu:
+        torch.backends.cudnn.benchmark = True   # codes/train.py:482
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):   # the reference prints its option dicts; stdout carries ONE JSON line
+        model, _ = RA.create_reference_model(torch_home=os.path.join(tempfile.gettempdir(), "b200_bench_ref_torch_home"),
+                                             precision=precision, nb=args.nb, hr_size=args.hr, use_gan=True,
+                                             use_fea=True, pixel_weight=1e-2, feature_weight=1.0, gan_weight=5e-3,
+                                             gpu=gpu, batch_size=batch)
+    return model
+
+
+def cpu_reference_steps(args, steps, warmup, threads=None, batch=1):
+    """The reference's own CPU path (gpu_ids null, fp32) on this box's host cores: feed_data +
+    optimize_parameters of the unmodified SRModel at `batch` images per step."""
+    from baseline import reference_arm as RA
     # oneDNN convolutions at batch 1 stop scaling (and oversubscribe badly) past a few dozen threads
-    torch.set_num_threads(threads or min(os.cpu_count(), 32))
-    torch.manual_seed(0)
-    g = RRDBNet_arch.RRDBNet(3, 3, 64, args.nb)
-    networks.init_weights(g, "kaiming", 0.1)
-    d = discriminators.Discriminator_VGG(args.hr, 3, 64)
-    networks.init_weights(d, "kaiming", 0.1)
-    tv = torch.load(vgg_checkpoint())
-    vgg_sd = O.torchvision_vgg_to_feature_net(tv)
-    orc = O.ESRGANStepOracle(OrderedDict(g.state_dict()), args.nb, OrderedDict(d.state_dict()), args.hr, vgg_sd)
-    gen = torch.Generator().manual_seed(1234)
-    lr_img = torch.rand(1, 3, args.hr // 4, args.hr // 4, generator=gen)
-    hr_img = torch.rand(1, 3, args.hr, args.hr, generator=gen)
-    for _ in range(warmup):
-        orc.optimize_parameters(lr_img, hr_img)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        orc.optimize_parameters(lr_img, hr_img)
-    dt = (time.perf_counter() - t0) / steps
-    return 1.0 / dt, dt, torch.get_num_threads()
+    torch.set_num_threads(threads or int(os.environ.get("B200_REF_THREADS", min(os.cpu_count(), 32))))
+    model = reference_model(args, False, "fp32", batch)
+    ms = RA.time_reference(model, reference_batch(args, batch), steps, warmup, cuda=False)
+    return batch / (ms / 1e3), ms / 1e3, torch.get_num_threads()
 
 
 def run_reference_cpu(args):
+    """Driver's reference arm: the unmodified reference on the host cores.  One 16-image step is
+    ~12 TFLOP (~25 s on 32 cores), so each step is a bounded sample of the workload: ONE image of the
+    batch (same networks, losses and sizes), K timed steps after W warm-ups."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 8))
-    ips, dt, threads = cpu_reference_steps(args, steps, max(1, min(args.warmup, 1)))
+    ips, dt, threads = cpu_reference_steps(args, args.steps, args.warmup)
     val = ips * args.hr * args.hr
-    sample = "batch 1 per step, %d timed steps (bounded sample of the %d-image step)" % (steps, args.batch)
+    sample = "1 image per step (bounded sample of the %d-image step), %d timed steps after %d warm-ups, fp32" % (
+        args.batch, args.steps, args.warmup)
     line = {"impl": "reference", "metric": "hr_pixels_per_sec", "value": val, "unit": "HR-px/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "images_per_sec": ips,
-            "config": {"workload": "ESRGAN 4x G/D step nb=%d HR %d^2 (oracle port of the reference, CPU)" % (args.nb, args.hr),
-                       "global_batch": 1},
-            "cpu_baseline": {"value": val, "unit": "HR-px/s", "cores": threads, "kind": "port", "sample": sample},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "images_per_sec": ips,
+            "config": {"workload": "ESRGAN 4x G/D step: RRDBNet nb=%d nf=64 + VGG19 conv5_4 L1 + Discriminator_VGG(%d) "
+                                   "RaGAN, L1 pixel; LR %d^2 -> HR %d^2 -- unmodified reference SRModel on CPU" %
+                                   (args.nb, args.hr, args.hr // 4, args.hr),
+                       "global_batch": 1, "per_gpu_batch": 1, "parallelism": "cpu"},
+            "cpu_baseline": {"value": val, "unit": "HR-px/s", "cores": threads, "kind": "reference", "sample": sample},
             "e2e": {"value": val, "unit": "HR-px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0,
+            # this arm runs the reference only: neither the product package nor the oracle may be in the process
+            "loaded": {m: any(k == m or k.startswith(m + ".") for k in sys.modules) for m in ("trainner_b200", "oracle")}}
+    assert not any(line["loaded"].values()), line["loaded"]
     print(json.dumps(line))
 
 
+def time_reference_cudnn(args, precision, steps, warmup):
+    """ms/step of the unmodified reference SRModel on this GPU through stock PyTorch/cuDNN
+    (gpu_ids [0], cudnn.benchmark as in codes/train.py:482).  precision: 'bf16' (bf16 autocast),
+    'amp' (the reference's native fp16 autocast + GradScaler, base_model.py:736-744) or 'fp32'."""
+    from baseline import reference_arm as RA
+    model = reference_model(args, True, precision, args.batch)
+    batch = reference_batch(args, args.batch, device="cuda")
+    ms = RA.time_reference(model, batch, steps, warmup, cuda=True)
+    del model
+    torch.cuda.empty_cache()
+    return ms
+
+
 def run_reference_cudnn(args):
-    """Context row (not the driver's reference arm): the reference's op sequence (oracle modules)
-    on the GPU through stock PyTorch/cuDNN under bf16 autocast -- what the reference does on a B200."""
-    from collections import OrderedDict
-    from oracle import esrgan_oracle as O
-    from trainner_b200 import networks
-    from trainner_b200.architectures import discriminators, RRDBNet_arch
-    torch.backends.cudnn.benchmark = True
-    torch.manual_seed(0)
-    g = RRDBNet_arch.RRDBNet(3, 3, 64, args.nb)
-    networks.init_weights(g, "kaiming", 0.1)
-    d = discriminators.Discriminator_VGG(args.hr, 3, 64)
-    networks.init_weights(d, "kaiming", 0.1)
-    vgg_sd = O.torchvision_vgg_to_feature_net(torch.load(vgg_checkpoint()))
-    orc = O.ESRGANStepOracle(OrderedDict(g.state_dict()), args.nb, OrderedDict(d.state_dict()), args.hr, vgg_sd,
-                             device="cuda")
-    gen = torch.Generator().manual_seed(1234)
-    lr_img = torch.rand(args.batch, 3, args.hr // 4, args.hr // 4, generator=gen).cuda()
-    hr_img = torch.rand(args.batch, 3, args.hr, args.hr, generator=gen).cuda()
-
-    def step():
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            orc.optimize_parameters(lr_img, hr_img)
-
-    ms = timed_steps(step, args.steps, args.warmup, 1)
+    """Context rows (not the driver's reference arm): what the reference itself does on a B200."""
+    rows = {}
+    for prec in ("bf16", "amp", "fp32"):
+        ms = time_reference_cudnn(args, prec, max(args.steps, 50) if prec != "fp32" else 10,
+                                  max(args.warmup, 20) if prec != "fp32" else 5)
+        rows[prec] = {"ms_per_step": ms, "images_per_sec": args.batch / (ms / 1e3)}
+    ms = rows["bf16"]["ms_per_step"]
     ips = args.batch / (ms / 1e3)
     print(json.dumps({"impl": "reference-cudnn", "metric": "hr_pixels_per_sec", "value": ips * args.hr ** 2,
-                      "unit": "HR-px/s", "images_per_sec": ips, "ms_per_step": ms, "n_gpus": 1, "steps": args.steps,
-                      "warmup": args.warmup, "dtype": "bf16 autocast", "data": "synthetic",
-                      "config": {"workload": "reference op sequence via PyTorch/cuDNN, nb=%d batch %d HR %d^2" %
+                      "unit": "HR-px/s", "images_per_sec": ips, "ms_per_step": ms, "n_gpus": 1,
+                      "steps": max(args.steps, 50), "warmup": max(args.warmup, 20), "dtype": "bf16 autocast",
+                      "data": "synthetic", "rows": rows,
+                      "config": {"workload": "unmodified reference SRModel via PyTorch/cuDNN, nb=%d batch %d HR %d^2" %
                                  (args.nb, args.batch, args.hr)}}))
 
 
@@ -294,6 +308,7 @@ def main():
     # ---- roofline leg: one instrumented step, CUDA events around every kernel launch of the plans
     roof = None
     cpu_base = None
+    vs_cudnn = None
     if True:  # every rank runs the instrumented step (it contains the gradient all-reduce); rank 0 reports
         from trainner_b200 import runtime
         rows = []
@@ -346,9 +361,21 @@ def main():
                 "step_algorithmic_tflops": GFLOP_PER_IMAGE_STEP * 1e-3 * args.batch,
                 "step_frac_of_peak": (GFLOP_PER_IMAGE_STEP * 1e9 * (args.batch / (ms / 1e3))) / (peak * 1e12)}
         if not args.no_cpu_baseline and world == 1 and rank == 0:
-            c_ips, c_dt, threads = cpu_reference_steps(args, 2, 1)
+            c_ips, c_dt, threads = cpu_reference_steps(args, 6, 1)
             cpu_base = {"value": c_ips * px, "unit": "HR-px/s", "images_per_sec": c_ips, "cores": threads,
-                        "kind": "port", "sample": "2 timed steps at batch 1 (nb=%d, HR %d^2), fp32" % (args.nb, args.hr)}
+                        "kind": "reference",
+                        "sample": "unmodified reference SRModel on CPU, 6 timed steps after 1 warm-up at 1 image per step "
+                                  "(bounded sample of the %d-image step; nb=%d, HR %d^2), fp32" % (args.batch, args.nb, args.hr)}
+        if not args.no_cudnn_ref and world == 1 and rank == 0:
+            # the reference's own GPU path on THIS B200, same config: the >= 6x target of BASELINE.json is
+            # images/s of this repo over these rows (>= 20 warm-ups, >= 50 timed iterations each)
+            vs_cudnn = {}
+            for prec, label in (("bf16", "bf16_autocast"), ("amp", "fp16_amp_gradscaler")):
+                r_ms = time_reference_cudnn(args, prec, 50, 20)
+                vs_cudnn[label] = {"reference_ms_per_step": r_ms, "reference_images_per_sec": args.batch / (r_ms / 1e3),
+                                   "ratio": r_ms / ms, "ratio_e2e": r_ms / ms_e2e}
+            vs_cudnn["what"] = ("unmodified reference SRModel (baseline/_ref) on this GPU via PyTorch/cuDNN, "
+                                "cudnn.benchmark, 20 warm-ups + 50 timed steps; ratio = reference ms / this repo's ms")
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -363,7 +390,8 @@ def main():
                            "l2": "per-step working set (>2 GB of activations) exceeds the 126 MB L2; no explicit flush"},
                 "e2e": {"value": ips_e2e * px, "unit": "HR-px/s", "images_per_sec": ips_e2e, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * len(sink.get("log", {}))},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base}
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+                "vs_cudnn": vs_cudnn}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
