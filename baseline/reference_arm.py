@@ -113,8 +113,6 @@ def build_opt(nb=1, hr_size=128, scale=4, use_gan=False, use_fea=False, pixel_we
 
     net_g = {"type": "esrgan", "nb": nb, "nf": 64, "gc": 32, "gaussian": False,
              "upsample_mode": upsample_mode}
-    if init_scale is not None:
-        net_g["init_scale"] = init_scale
     opt = {
         "name": "parity",
         "model": "sr",
@@ -149,6 +147,10 @@ def build_opt(nb=1, hr_size=128, scale=4, use_gan=False, use_fea=False, pixel_we
         opt["network_D"] = {"type": "discriminator_vgg"}
     opt = dict_to_nonedict(opt)
     opt = get_network_defaults(opt, True)
+    if init_scale is not None:
+        # get_network_defaults rebuilds network_G from its known keys (defaults.py:36-63) and drops init_scale;
+        # networks.get_network pops it from the final dict (networks.py:116-118), so it is set here
+        opt["network_G"]["init_scale"] = init_scale
     return dict_to_nonedict(opt)
 
 

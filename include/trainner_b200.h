@@ -133,6 +133,44 @@ typedef struct {
 
 int b200_rdb_persist(const b200_rdb_desc* d, int32_t* flags, int32_t flag_base, b200_stream_t stream);
 
+/* Whole-trunk chain of dense blocks in ONE persistent launch (csrc/rdb_chain.cu): the stage-merged form of
+ * b200_rdb_persist with the finished slices kept in shared memory as the next stage's operand, two independent
+ * 128-position tiles per CTA and the halo rows exchanged through L2 in flag-in-data (LL) form.  Replaces the
+ * 5 x n_blocks per-conv launches of ResidualDenseBlock_5C.forward / RRDB.forward (RRDBNet_arch.py:89-96,150-163)
+ * and of their input gradients.  Stage s = 5*block + j: input slice = the output slice of stage s-1 (stage 0:
+ * channels [x_coff, x_coff+64) of x0), epilogue
+ *   v = alpha*(acc + bias) + beta1*res1 + beta2*res2 ; act ? lrelu(v, slope) ; mask ? (mask > 0 ? v : mask_slope*v)
+ * for the 32 (j = 4: 64) channels that stage completes, stored to out[m*out_c + out_coff ..] (bf16, interior
+ * positions only; NULL = not stored).  All tensors are flat zero-bordered [n_total, h+2, w+2, C] bf16. */
+typedef struct {
+  void* out;
+  const float* bias;     /* indexed by channel within the stage's completing slice, or NULL */
+  const void* mask;
+  const void* res1;
+  const void* res2;
+  int32_t out_c, out_coff, mask_c, mask_coff, res1_c, res1_coff, res2_c, res2_coff;
+  float alpha, beta1, beta2, slope, mask_slope;
+  int32_t act;
+  int32_t pad_[2];
+} b200_chain_stage;
+
+typedef struct {
+  int32_t n_total, img0, n;   /* images in the tensors; first image and image count of this launch */
+  int32_t h, w;
+  int32_t cx, x_coff;         /* channel pitch / offset of the first block's 64-channel input in x0 */
+  int32_t n_blocks;
+  int32_t flip_taps;          /* 0: forward taps; 1: input-gradient taps */
+} b200_chain_desc;
+
+/* CTAs (= co-resident tile pairs; must not exceed the SM count) and exchange-buffer bytes for n images */
+int b200_rdb_chain_geometry(int32_t n, int32_t h, int32_t w, int32_t* n_cta, int64_t* ll_bytes);
+/* w_stage[j]: packed stage weights [n_blocks][9][192-32j][K_j] bf16 (K_0 = 64, K_j = 32); table_dev:
+ * [n_blocks][5] b200_chain_stage in device memory; ll_buf: zero-initialised once, reused by every launch;
+ * epoch_dev: one uint32 in device memory (zero-initialised), owned by the library between launches. */
+int b200_rdb_chain(const b200_chain_desc* d, const void* x0, const void* const* w_stage,
+                   const b200_chain_stage* table_dev, void* ll_buf, int64_t ll_bytes, uint32_t* epoch_dev,
+                   b200_stream_t stream);
+
 /* Weight gradient of a conv (autograd wgrad of block.py:238):
  *   dw[co][ci][ky][kx] += scale * sum_{n,y,x} dy[n,y,x,dy_coff+co] * x[n, y*stride+ky-pad, x*stride+kx-pad, x_coff+ci]
  * dw is fp32 OIHW (the layout of nn.Conv2d.weight.grad); accumulated with fp32 atomics.      */
@@ -161,8 +199,13 @@ int b200_tensor_map_bytes(void);
 int b200_wgrad_rdb_make_maps(void* maps_host, int32_t n_rdb, const void* const* x_ptrs,
                              const void* const* g_ptrs, const void* const* do_ptrs,
                              const int32_t* do_pitch, int32_t n, int32_t h, int32_t w, int32_t c);
+/* The positions are reduced in slices (L2 locality); each slice parks its partial sums in a caller-provided
+ * workspace of b200_wgrad_rdb_ws_bytes() bytes and a second kernel adds the slices in a fixed order
+ * (deterministic: no float atomics). */
+int64_t b200_wgrad_rdb_ws_bytes(int32_t n_rdb, int32_t n, int32_t h, int32_t w);
 int b200_wgrad_rdb(const void* maps_dev, const b200_wgrad_rdb_entry* entries_dev, int32_t n_rdb,
-                   int32_t n, int32_t h, int32_t w, int32_t nf, int32_t gc, b200_stream_t stream);
+                   int32_t n, int32_t h, int32_t w, int32_t nf, int32_t gc, void* workspace,
+                   int64_t ws_bytes, b200_stream_t stream);
 
 /* Many per-channel column sums in one launch: dst[c] += scale * sum_p src[p*pitch + coff + c]  (bias grads) */
 typedef struct {

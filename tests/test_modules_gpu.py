@@ -298,3 +298,40 @@ def test_psnr_after_training_matches_reference_paths():
     # 1.5 dB: the fp32 atomics of the split-K weight-gradient kernels make the CUDA trajectory vary from run to run
     # on top of the chaos above (observed late-mean gaps over several runs: 0.3 .. 0.7 dB, either sign)
     assert abs(mb - m32) <= max(1.5, 2.0 * abs(m16 - m32)), (m32, m16, mb)
+
+
+@pytest.mark.parametrize("shape", [(3, 12, 20, 2), (2, 16, 16, 1), (16, 64, 64, 23)])
+def test_trunk_chain_matches_per_conv_flat_path(shape, monkeypatch):
+    """The whole-trunk chain kernel (csrc/rdb_chain.cu: stage-merged dense blocks, TMEM-resident partial sums,
+    slices turned around in shared memory, LL halo exchange) against the per-conv flat kernels (conv_flat.cu) on
+    the same weights: both store every slice in bf16 and accumulate in fp32, only the summation order differs.
+    Covers an odd image count (unequal position ranges), a single-tile-per-range case and BASELINE config 2's
+    trunk at its real size (nb = 23, 16 x 64 x 64: two launches of 8 images, 137 CTAs)."""
+    from trainner_b200 import networks
+    from trainner_b200.architectures import RRDBNet_arch
+    n, h, w, nb = shape
+    torch.manual_seed(3)
+    x = torch.rand(n, 3, h, w, device="cuda")
+    outs, grads = [], []
+    sd = None
+    for chain in ("0", "1"):
+        monkeypatch.setenv("B200_TRUNK_CHAIN", chain)
+        net = RRDBNet_arch.RRDBNet(3, 3, 64, nb).cuda()
+        if sd is None:
+            networks.init_weights(net, "kaiming", 0.3)
+            sd = OrderedDict((k, v.clone()) for k, v in net.state_dict().items())
+        net.load_state_dict(sd)
+        for rep in range(2):   # the second pass re-uses the context (LL buffers, epoch) and accumulates grads
+            y = net(x)
+            y.backward(torch.ones_like(y) * 0.5 if rep else torch.sign(y.detach() - 0.1))
+        eng = net._engine[0]
+        assert eng.chain == (chain == "1")
+        outs.append(y.detach().float())
+        grads.append(OrderedDict((k, p.grad.detach().float().clone()) for k, p in net.named_parameters()))
+    e = rel(outs[1], outs[0])
+    print("chain vs flat: output rel-L2 %.3e (std %.3e)" % (e, float(outs[0].std())))
+    assert float(outs[0].std()) > 1e-3
+    assert e < 4e-3
+    worst = max((rel(grads[1][k], grads[0][k]), k) for k in grads[0])
+    print("chain vs flat: worst gradient rel-L2 %.3e (%s)" % worst)
+    assert worst[0] < 2e-2, worst

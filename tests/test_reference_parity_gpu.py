@@ -7,14 +7,23 @@ runs ON THE SAME GPU through PyTorch/cuDNN twice -- fp32 (TF32 off) = the ground
 bf16 autocast = the reference's own reduced-precision path, the like-for-like yardstick -- and
 trainner_b200 runs the identical step from identical weights on the identical batch.
 
-Tolerances (no absolute floors):
-  * every log_dict scalar: |v - v_ref32| <= 2e-2 |v_ref32|;
+Tolerances (no absolute floors on the scalars):
+  * the log_dict scalars pix-l1, fea-vgg19-l1, l_g_gan, l_d_real, l_d_fake, D_real:
+    |v - v_ref32| <= 2e-2 |v_ref32|;
+  * D_fake / D_real are MEANS of 16 raw logits that nearly cancel (measured: mean -7e-3, std 7e-3), and D(fake)
+    amplifies the ~1.3e-2 relative bf16 error of the SR input through ten BatchNorm layers: the reference's OWN
+    bf16 path misses 2e-2 on D_fake (measured 2.5e-2).  They are therefore checked where the noise can be
+    measured, per logit: the step's D(fake) / D(real) forwards are repeated from the initial weights and
+    rms(logit error) of the CUDA path must be <= 1.25 x that of the reference's bf16 path; the logged means must be
+    within max(2e-2 |v|, 3 sigma) with sigma = rms(reference-bf16 logit error) / sqrt(16);
   * SR (fake_H): rel-L2 vs reference-fp32 <= max(1e-2, 1.25 x the reference-bf16 rel-L2);
-  * every gradient tensor of G and D: rel-L2 error vs reference-fp32 <= 1.25 x the error of the
-    reference's bf16 path on that tensor (tensors whose reference-fp32 gradient is numerically zero --
-    conv biases in front of BatchNorm -- are compared by absolute size instead);
-  * every updated parameter tensor: the Adam update (p_after - p_before) vs the reference-fp32
-    update, same 1.25 x yardstick.
+  * every gradient tensor of G and D: rel-L2 error vs reference-fp32 <= 1.25 x the error of the reference's
+    bf16 path on that tensor (fp32-rounding-level errors <= 1e-5 pass);
+  * every updated parameter tensor: Adam's first update is -lr * sign(g) wherever |g| >> eps, so the error of an
+    update is a COUNT of sign flips (elements whose gradient is within the rounding noise of zero); per tensor
+    flips <= 1.25 x flips of the reference-bf16 path + 3 + 3 sqrt(flips_ref) (Poisson slack for small tensors),
+    and over all tensors of a network flips <= 1.1 x the reference-bf16 total; BatchNorm running statistics and
+    num_batches_tracked directly.
 G uses network_G.init_scale 0.3 (the reference's option, networks.py:116-120): with the default
 0.1 an untrained 23-block G outputs ~1e-4 and every comparison would be vacuous.
 """
@@ -131,12 +140,33 @@ def _compare_tensors(what, ours, ref16, ref32, zero_abs):
         e, e_ref = rel(ours[k], t32), rel(ref16[k], t32)
         e_all.append(e)
         e_ref_all.append(e_ref)
-        if e > 1.25 * e_ref:
+        if e > max(1.25 * e_ref, 1e-5):
             bad.append((k, e, e_ref))
-    print("%s: %d tensors, mean rel-err trainner_b200 %.4f | reference bf16 %.4f; worst ratio %.2f" %
-          (what, len(e_all), sum(e_all) / len(e_all), sum(e_ref_all) / len(e_ref_all),
-           max(a / b for a, b in zip(e_all, e_ref_all))))
+    med = lambda v: sorted(v)[len(v) // 2]  # noqa: E731
+    print("%s: %d tensors, median rel-err trainner_b200 %.4f | reference bf16 %.4f; worst ratio %.2f" %
+          (what, len(e_all), med(e_all), med(e_ref_all), max(a / max(b, 1e-30) for a, b in zip(e_all, e_ref_all))))
     return bad
+
+
+def _discriminator_logits(r32, r16, ours, batch):
+    """The D-step's forwards (losses.py:471-478: netD(fake.detach()), netD(real)) repeated from the initial D
+    weights on each path's own fake_H: reference fp32, reference bf16 autocast, trainner_b200."""
+    from models.modules.architectures import discriminators as ref_disc
+    from trainner_b200.architectures import discriminators as b200_disc
+    dref = ref_disc.Discriminator_VGG(HR, 3, 64).cuda()
+    db = b200_disc.Discriminator_VGG(HR, 3, 64).cuda()
+    out = {}
+    with torch.no_grad():
+        for key, x32, x16, xb in (("fake", r32["sr"], r16["sr"], ours["sr"]), ("real", batch["HR"], batch["HR"], batch["HR"])):
+            dref.load_state_dict(r32["d0"]); dref.train()
+            l32 = dref(x32).float().flatten().double()
+            dref.load_state_dict(r32["d0"])
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                l16 = dref(x16).float().flatten().double()
+            db.load_state_dict(r32["d0"]); db.train()
+            lb = db(xb).float().flatten().double()
+            out[key] = (l32, l16, lb)
+    return out
 
 
 @needs_ref
@@ -153,26 +183,63 @@ def test_full_size_step_vs_unmodified_reference():
     print("log_dict (reference fp32 | reference bf16 | trainner_b200):")
     for k, a, b, c in rows:
         print("  %-14s % .6e  % .6e (rel %.2e)  % .6e (rel %.2e)" % (k, a, b, abs(b - a) / abs(a), c, abs(c - a) / abs(a)))
+    problems = []
     for k, a, b, c in rows:
-        assert abs(c - a) <= 2e-2 * abs(a), (k, a, c)
+        if k in ("D_real", "D_fake"):
+            continue   # checked per logit below
+        if not abs(c - a) <= 2e-2 * abs(a):
+            problems.append(("log", k, a, c))
+    # ---- D_real / D_fake: repeat the D-step's forwards (initial D weights, the step's own fake_H) per logit
+    logit_rows = _discriminator_logits(r32, r16, ours, batch)
+    for name, key in (("D_fake", "fake"), ("D_real", "real")):
+        l32, l16, lb = logit_rows[key]
+        e16, eb = float((l16 - l32).pow(2).mean().sqrt()), float((lb - l32).pow(2).mean().sqrt())
+        sigma = e16 / (l32.numel() ** 0.5)
+        a, c = r32["logs"][0][name], ours["logs"][0][name]
+        print("%s logits: mean %.4e std %.3e | rms error reference-bf16 %.3e, trainner_b200 %.3e | logged mean off by "
+              "%.3e (%.1f sigma)" % (name, float(l32.mean()), float(l32.std()), e16, eb, abs(c - a), abs(c - a) / sigma))
+        assert abs(float(l32.mean()) - a) <= 1e-4 * abs(a) + 1e-7, "the repeated forward must reproduce the logged mean"
+        if not eb <= 1.25 * e16:
+            problems.append(("logits", name, eb, e16))
+        if not abs(c - a) <= max(2e-2 * abs(a), 3.0 * sigma):
+            problems.append(("log", name, a, c, sigma))
     # ---- SR
     e_sr, e_sr16 = rel(ours["sr"], r32["sr"]), rel(r16["sr"], r32["sr"])
     print("SR rel-L2: trainner_b200 %.4e | reference bf16 %.4e; SR std %.3e" % (e_sr, e_sr16, float(r32["sr"].std())))
-    assert float(r32["sr"].std()) > 1e-2, "degenerate generator output"
-    assert e_sr <= max(1e-2, 1.25 * e_sr16)
+    assert float(r32["sr"].std()) > 1e-2, "degenerate generator output (init_scale not applied?)"
+    if not e_sr <= max(1e-2, 1.25 * e_sr16):
+        problems.append(("sr", e_sr, e_sr16))
     # ---- gradients, every tensor
     for net in ("G", "D"):
         bad = _compare_tensors("grad " + net, ours["grads"][net], r16["grads"][net], r32["grads"][net], 1e-9)
-        assert not bad, (net, len(bad), bad[:8])
-    # ---- every updated parameter tensor (and BatchNorm running statistics)
+        if bad:
+            problems.append(("grad " + net, len(bad), bad[:8]))
+    # ---- every updated parameter tensor (sign flips of Adam's first update) and the BatchNorm running statistics
+    lr = 1e-4
     for net, k0, k1 in (("G", "g0", "g1"), ("D", "d0", "d1")):
-        upd = lambda r, ref=r32, k0=k0, k1=k1: OrderedDict(  # noqa: E731
-            (k, (r[k1][k].double() - ref[k0][k].double())) for k in ref[k0] if ref[k0][k].is_floating_point())
-        bad = _compare_tensors("update " + net, upd(ours), upd(r16), upd(r32), 1e-12)
-        assert not bad, (net, len(bad), bad[:8])
-        for k, v in r32[k1].items():
-            if not v.is_floating_point():
-                assert int(ours[k1][k]) == int(v), k   # num_batches_tracked
+        tot_o = tot_r = 0
+        for k, p0 in r32[k0].items():
+            if not p0.is_floating_point():
+                assert int(ours[k1][k]) == int(r32[k1][k]), k   # num_batches_tracked
+                continue
+            u32 = r32[k1][k].double() - p0.double()
+            if "running_" in k:
+                eo, er = rel(ours[k1][k].double() - p0.double(), u32), rel(r16[k1][k].double() - p0.double(), u32)
+                if not eo <= max(1.25 * er, 1e-5):
+                    problems.append(("bn stat", k, eo, er))
+                continue
+            fo = int(((ours[k1][k].double() - p0.double() - u32).abs() > lr).sum())
+            fr = int(((r16[k1][k].double() - p0.double() - u32).abs() > lr).sum())
+            tot_o += fo
+            tot_r += fr
+            if fo > 1.25 * fr + 3 + 3 * fr ** 0.5:
+                problems.append(("update " + net, k, fo, fr, p0.numel()))
+        n_el = sum(v.numel() for v in r32[k0].values() if v.is_floating_point())
+        print("update %s: sign flips of Adam's first update vs reference fp32: trainner_b200 %d | reference bf16 %d of %d "
+              "elements" % (net, tot_o, tot_r, n_el))
+        if tot_o > 1.1 * tot_r + 10:
+            problems.append(("update total " + net, tot_o, tot_r))
+    assert not problems, problems
 
 
 @needs_ref
@@ -194,7 +261,7 @@ def test_reference_srmodel_drives_b200_modules_full_size():
         from trainner_b200.architectures import RRDBNet_arch, discriminators, perceptual
         assert isinstance(RA.unwrap(model.netG), RRDBNet_arch.RRDBNet)
         assert isinstance(RA.unwrap(model.netD), discriminators.Discriminator_VGG)
-        assert isinstance(RA.perceptual_network(model), perceptual.FeatureExtractor)
+        assert isinstance(RA.unwrap(RA.perceptual_network(model)), perceptual.FeatureExtractor)
         RA.unwrap(model.netG).load_state_dict(stock["g0"])
         RA.unwrap(model.netD).load_state_dict(stock["d0"])
         logs = []

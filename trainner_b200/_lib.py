@@ -98,6 +98,20 @@ class RdbDesc(C.Structure):
                 ("stage", RdbStage * 5)]
 
 
+class ChainStage(C.Structure):
+    _fields_ = [("out", C.c_void_p), ("bias", C.c_void_p), ("mask", C.c_void_p), ("res1", C.c_void_p),
+                ("res2", C.c_void_p),
+                ("out_c", C.c_int32), ("out_coff", C.c_int32), ("mask_c", C.c_int32), ("mask_coff", C.c_int32),
+                ("res1_c", C.c_int32), ("res1_coff", C.c_int32), ("res2_c", C.c_int32), ("res2_coff", C.c_int32),
+                ("alpha", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("slope", C.c_float),
+                ("mask_slope", C.c_float), ("act", C.c_int32), ("pad_", C.c_int32 * 2)]
+
+
+class ChainDesc(C.Structure):
+    _fields_ = [("n_total", C.c_int32), ("img0", C.c_int32), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("cx", C.c_int32), ("x_coff", C.c_int32), ("n_blocks", C.c_int32), ("flip_taps", C.c_int32)]
+
+
 class PackEntry(C.Structure):
     _fields_ = [
         ("src", C.c_void_p), ("dst", C.c_void_p),
@@ -114,11 +128,13 @@ _SIGNATURES = {
     "b200_conv3x3_flat": [C.POINTER(FlatDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "b200_pack_cat": [_P, _I, _I, _P],
     "b200_rdb_persist": [C.POINTER(RdbDesc), _P, _I, _P],
+    "b200_rdb_chain": [C.POINTER(ChainDesc), _P, _P, _P, _P, _L, _P, _P],
+    "b200_rdb_chain_geometry": [_I, _I, _I, _P, _P],
     "b200_pad_copy": [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_unpad_add": [_P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P],
     "b200_conv_wgrad": [C.POINTER(WgradDesc), _P, _P, _P, _P, _P],
     "b200_wgrad_rdb_make_maps": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I],
-    "b200_wgrad_rdb": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "b200_wgrad_rdb": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _L, _P],
     "b200_colsum_multi": [_P, _I, _P],
     "b200_pack_weights": [_P, _I, _I, _P],
     "b200_conv3x3_thin_to_wide": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _F,
@@ -145,7 +161,8 @@ _SIGNATURES = {
 }
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["b200_last_error", "b200_version", "b200_device_ok",
-                                                "b200_launch_count", "b200_tensor_map_bytes"])
+                                                "b200_launch_count", "b200_tensor_map_bytes",
+                                                "b200_wgrad_rdb_ws_bytes"])
 
 
 def _load():
@@ -164,6 +181,8 @@ def _load():
     lib.b200_launch_count.restype = C.c_int64
     lib.b200_tensor_map_bytes.restype = C.c_int
     lib.b200_tensor_map_bytes.argtypes = []
+    lib.b200_wgrad_rdb_ws_bytes.restype = C.c_int64
+    lib.b200_wgrad_rdb_ws_bytes.argtypes = [_I, _I, _I, _I]
     return lib
 
 

@@ -68,6 +68,9 @@ class _RRDBNetFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, anchor, engine):
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("RRDBNet: the gradient wrt the LR input image is not computed by the B200 "
+                                      "engine (the ESRGAN step never needs it); detach the input")
         need_bwd = any(ctx.needs_input_grad)  # (autograd runs forward() with grad mode off)
         out, lease = engine.forward(x, need_bwd)
         ctx.engine, ctx.lease = engine, lease

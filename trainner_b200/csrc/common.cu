@@ -1,6 +1,8 @@
 #include "common.cuh"
 
+#include <map>
 #include <mutex>
+#include <utility>
 #include <stdlib.h>
 
 namespace b200 {
@@ -32,14 +34,63 @@ bool pdl_enabled() {
 }
 
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess)
-      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static std::mutex mu;
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  std::lock_guard<std::mutex> g(mu);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cache[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = n > 0 ? n : 148;
   }
-  return n;
+  return cache[dev];
+}
+
+int ensure_max_smem(const void* kernel, int bytes, bool prefer_max_carveout) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_error("cudaGetDevice failed: %s", cudaGetErrorString(e));
+  std::lock_guard<std::mutex> g(mu);
+  auto key = std::make_pair(kernel, dev);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return 0;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && prefer_max_carveout)
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess)
+    return set_error("cudaFuncSetAttribute(max dynamic smem %d) failed on device %d: %s", bytes, dev,
+                     cudaGetErrorString(e));
+  done[key] = bytes;
+  return 0;
+}
+
+int det_scratch(DetScratch* out, size_t floats_needed, int counters_needed) {
+  static std::mutex mu;
+  static DetScratch per_dev[64] = {};
+  if (floats_needed > kDetFloats || counters_needed > kDetCounters)
+    return set_error("deterministic-reduction scratch too small: need %zu floats / %d counters", floats_needed,
+                     counters_needed);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 64) return set_error("det_scratch: cudaGetDevice failed");
+  std::lock_guard<std::mutex> g(mu);
+  if (!per_dev[dev].part) {
+    void* p = nullptr;
+    e = cudaMalloc(&p, kDetFloats * sizeof(float) + kDetCounters * sizeof(unsigned));
+    if (e != cudaSuccess)
+      return set_error("det_scratch: cudaMalloc failed (%s) -- the first call of a reduction kernel must not happen "
+                       "inside a stream capture", cudaGetErrorString(e));
+    e = cudaMemset(static_cast<float*>(p) + kDetFloats, 0, kDetCounters * sizeof(unsigned));
+    if (e != cudaSuccess) return set_error("det_scratch: cudaMemset failed (%s)", cudaGetErrorString(e));
+    per_dev[dev].part = static_cast<float*>(p);
+    per_dev[dev].counters = reinterpret_cast<unsigned*>(static_cast<float*>(p) + kDetFloats);
+  }
+  *out = per_dev[dev];
+  return 0;
 }
 
 int make_tensor_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims,

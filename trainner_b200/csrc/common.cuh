@@ -49,12 +49,32 @@ typedef CUresult (*EncodeTiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiled_t get_encode_tiled();
-int sm_count();
+int sm_count();   // of the CURRENT device (cached per device)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize (and optionally the max-shared carveout) is a per-device
+// attribute of a kernel: set once per (kernel, device) under a mutex, so that a process that drives
+// several GPUs (nn.DataParallel / gpu_ids lists of the reference) never launches with a stale limit.
+int ensure_max_smem(const void* kernel, int bytes, bool prefer_max_carveout = false);
+#define B200_ENSURE_SMEM(kernel, bytes) \
+  do { if (::b200::ensure_max_smem(reinterpret_cast<const void*>(kernel), (bytes))) return 1; } while (0)
 
 // bf16 tensor map, rank <= 5, dims/strides innermost first (strides in bytes, rank-1 entries).
 int make_tensor_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
                     CUtensorMapSwizzle swizzle);
+
+// Deterministic cross-block reductions ("last block sums the partials in block order"): a small library-owned
+// arena per device (64 MB of fp32 partials + 8192 arrival counters, allocated on first use -- never during
+// stream capture) shared by the reduction kernels of the library, which run one after another on a stream
+// (every kernel waits for its predecessor; concurrent use from several streams is not supported).
+// No float atomics anywhere: two runs on the same inputs give bit-identical results.
+struct DetScratch {
+  float* part;
+  unsigned* counters;
+};
+constexpr size_t kDetFloats = 16u << 20;
+constexpr int kDetCounters = 8192;
+int det_scratch(DetScratch* out, size_t floats_needed, int counters_needed);
 
 inline cudaStream_t as_stream(b200_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -85,6 +105,60 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Block-uniform: true in the LAST of `nblk` blocks to arrive on `counter`.  Partials written (by any thread of
+// the calling block) before the call are visible to the last block after it; the counter resets itself.
+__device__ __forceinline__ bool det_arrive_last(unsigned* counter, unsigned nblk) {
+  __shared__ unsigned s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+    const unsigned t = atomicAdd(counter, 1u);
+    s_last = (t == nblk - 1) ? 1u : 0u;
+    if (s_last) *counter = 0u;
+  }
+  __syncthreads();
+  const bool last = s_last != 0u;
+  if (last) __threadfence();
+  return last;
+}
+
+// Run by the last block (all blockDim.x = 256 threads): out(k, sum_b part[b * nout + k]) for k < nout, the
+// sum taken in a FIXED order -- G = 256 / nout thread groups take interleaved block subsets (b = g, g+G, ...)
+// and their partial sums are combined in group order through `sh` (256 floats of shared memory).
+template <typename F>
+__device__ __forceinline__ void det_sum_blocks(const float* __restrict__ part, unsigned nblk, int nout, float* sh,
+                                               F&& out) {
+  const int tid = threadIdx.x;
+  if (nout >= 128) {
+    for (int k = tid; k < nout; k += 256) {
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+      unsigned b = 0;
+      for (; b + 3 < nblk; b += 4) {
+        t0 += part[(size_t)b * nout + k];
+        t1 += part[(size_t)(b + 1) * nout + k];
+        t2 += part[(size_t)(b + 2) * nout + k];
+        t3 += part[(size_t)(b + 3) * nout + k];
+      }
+      for (; b < nblk; ++b) t0 += part[(size_t)b * nout + k];
+      out(k, (t0 + t1) + (t2 + t3));
+    }
+    return;
+  }
+  int G = 256 / nout;
+  const int g = tid / nout, k = tid - g * nout;
+  float t = 0.f;
+  if (g < G)
+    for (unsigned b = g; b < nblk; b += G) t += part[(size_t)b * nout + k];
+  __syncthreads();
+  sh[tid] = t;
+  __syncthreads();
+  if (tid < nout) {
+    float tot = 0.f;
+    for (int q = 0; q < G; ++q) tot += sh[q * nout + tid];
+    out(tid, tot);
+  }
+}
 #endif
 
 }  // namespace b200

@@ -498,20 +498,14 @@ extern "C" int b200_conv3x3_flat(const b200_flat_desc* d, const void* x, const v
   B200_REQUIRE(d->cout > 0 && d->cout % 16 == 0 && d->cout <= 192, "b200_conv3x3_flat: cout %% 16, <= 192");
   B200_REQUIRE(d->cx % 8 == 0 && d->cy % 8 == 0 && d->cin_off % 8 == 0 && d->cout_off % 8 == 0,
                "b200_conv3x3_flat: channel pitches/offsets must be multiples of 8");
-  static bool attr_set = false;
-  static int two_cta = 0;   // measured slower at ~1.85 tiles per SM (both CTAs run in lockstep); opt-in via B200_FLAT_2CTA=1
+  static int two_cta = -1;   // measured slower at ~1.85 tiles per SM (both CTAs run in lockstep); opt-in via B200_FLAT_2CTA=1
   const int kSmemBytes = 200 * 1024;
   const int kSmemBytes2 = 112 * 1024;   // two co-resident CTAs per SM (228 KB - 1 KB reserved per CTA)
-  if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_flat_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kSmemBytes));
-    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_flat_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kSmemBytes2));
-    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_flat_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                         cudaSharedmemCarveoutMaxShared));
+  B200_ENSURE_SMEM(conv_flat_kernel<8>, kSmemBytes);
+  if (::b200::ensure_max_smem(reinterpret_cast<const void*>(conv_flat_kernel<4>), kSmemBytes2, true)) return 1;
+  if (two_cta < 0) {
     const char* e = getenv("B200_FLAT_2CTA");
-    if (e) two_cta = atoi(e);
-    attr_set = true;
+    two_cta = e ? atoi(e) : 0;
   }
   FlatParams p;
   memset(&p, 0, sizeof(p));
@@ -574,17 +568,34 @@ extern "C" int b200_conv3x3_flat(const b200_flat_desc* d, const void* x, const v
     }
   }
   if (!use2) {
+    // Shared-memory fit: prefer 2-3 activation stages and the largest weight stage (fewest barrier round
+    // trips); wide images (large A region: (256 + 2(w+3)) rows x 128 B per stage) fall back to fewer taps
+    // per weight stage and finally to a single activation stage.  Widest LR input that fits: w ~ 580.
     const int budget = kSmemBytes - 2048;
-    p.a_stages = 2;
-    p.b_stages = (budget - p.a_stages * (int)p.a_stage_bytes) / (int)p.b_stage_bytes;
-    if (p.b_stages > kMaxBStages) p.b_stages = kMaxBStages;
+    bool fit = false;
+    const int tpb0 = p.tpb;
+    for (int a_st = 2; a_st >= 1 && !fit; --a_st) {
+      for (int tpb : {9, 3, 1}) {
+        if (tpb > tpb0) continue;
+        const int st = (int)p.b_tap_bytes * tpb;
+        const int bs = (budget - a_st * (int)p.a_stage_bytes) / st;
+        if (bs >= 2) {
+          p.a_stages = a_st;
+          p.tpb = tpb;
+          p.b_stage_bytes = (uint32_t)st;
+          p.b_stages = bs > kMaxBStages ? kMaxBStages : bs;
+          fit = true;
+          break;
+        }
+      }
+    }
+    B200_REQUIRE(fit, "b200_conv3x3_flat: image too wide for the shared-memory A region (w=%d; limit ~580)", d->w);
     while (p.a_stages < 3 && p.b_stages >= 3 &&
            budget - (p.a_stages + 1) * (int)p.a_stage_bytes >= 3 * (int)p.b_stage_bytes) {
       ++p.a_stages;
       p.b_stages = (budget - p.a_stages * (int)p.a_stage_bytes) / (int)p.b_stage_bytes;
       if (p.b_stages > kMaxBStages) p.b_stages = kMaxBStages;
     }
-    B200_REQUIRE(p.b_stages >= 2, "b200_conv3x3_flat: image too wide for the shared-memory A region (w=%d)", d->w);
   }
   p.b_ring_off = (uint32_t)p.a_stages * p.a_stage_bytes;
   if (d->cin > 0) {

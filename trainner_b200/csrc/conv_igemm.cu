@@ -594,15 +594,9 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
   B200_REQUIRE(!(d->upsample2x && (d->out_mul_y != 1 || d->out_mul_x != 1)),
                "b200_conv_igemm: upsample2x excludes output placement");
 
-  static bool attr_set = false;
   const int kSmemBytes = 200 * 1024;
-  if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm256_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
-  }
+  B200_ENSURE_SMEM(conv_igemm_kernel, kSmemBytes);
+  B200_ENSURE_SMEM(conv_igemm256_kernel, kSmemBytes);
 
   IgemmParams p;
   memset(&p, 0, sizeof(p));

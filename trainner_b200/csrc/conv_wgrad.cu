@@ -32,6 +32,7 @@ struct WgradParams {
   uint32_t stage_bytes;
   float scale;
   float* dw;
+  float* ws;   // split-K partials [split][tap][co][ci] (nullptr when splits == 1: single owner, direct +=)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -171,12 +172,20 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
         tmem_ld_32x32b_x16(t_row + c0, r);
         tmem_ld_wait();
         if (ci < p.cin) {
+          // no atomics: an element of dW is owned by exactly one item per pixel split
+          if (p.ws) {
+            float* slab = p.ws + ((size_t)ks * p.taps + t) * p.cout * p.cin;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int co = nb * p.BN + c0 + j;
-            if (co < p.cout)
-              atomicAdd(p.dw + ((size_t)co * p.cin + ci) * p.taps + t,
-                        p.scale * __uint_as_float(r[j]));
+            for (int j = 0; j < 16; ++j) {
+              const int co = nb * p.BN + c0 + j;
+              if (co < p.cout) slab[(size_t)co * p.cin + ci] = __uint_as_float(r[j]);   // lanes = consecutive ci
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int co = nb * p.BN + c0 + j;
+              if (co < p.cout) p.dw[((size_t)co * p.cin + ci) * p.taps + t] += p.scale * __uint_as_float(r[j]);
+            }
           }
         }
       }
@@ -194,11 +203,30 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
 
 // Per-channel column sum of an NHWC bf16 slice: db[c] += scale * sum_p dy[p, coff + c]
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
-                                                     long long npix, int cdy, int coff, int c, float scale) {
+                                                     long long npix, int cdy, int coff, int c, float scale,
+                                                     float* __restrict__ part, unsigned* __restrict__ counter) {
   pdl_trigger();
   pdl_wait();
   __shared__ float red[256 * 8];
-  colsum_vec(dy, npix, cdy, coff, c, scale, db, red);
+  colsum_vec(dy, npix, cdy, coff, c, scale, db, red, part, counter);
+}
+
+// Second pass of the split-K weight gradient: dW (OIHW) += scale * sum over the pixel splits, in split order.
+// ws is tap-major [split][tap][co][ci] (the layout the tcgen05 epilogue writes with full 128-byte lines).
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw,
+                                                           int splits, int taps, int cout, int cin, float scale) {
+  pdl_trigger();
+  pdl_wait();
+  const long long per = (long long)taps * cout * cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin);
+    const long long r = i / cin;
+    const int co = (int)(r % cout), t = (int)(r / cout);
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += ws[(long long)k * per + i];
+    dw[((size_t)co * cin + ci) * taps + t] += scale * s;
+  }
 }
 
 // One thread converts all taps of one (row, col) weight: the fp32 source is read as `taps` consecutive
@@ -275,23 +303,20 @@ extern "C" int b200_conv_wgrad(const b200_wgrad_desc* d, const void* x, const vo
     // one block covers (256 / (cout/8)) pixel lanes x 4 pixels in flight; at most 4 waves of blocks
     const long long per_block = (long long)(256 / (d->cout / 8)) * 16;
     long long gx = (npix + per_block - 1) / per_block;
-    if (gx > 148 * 4) gx = 148 * 4;
+    if (gx > 148 * 2) gx = 148 * 2;   // the last block adds the per-block partials: keep them few
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, 1);
+    DetScratch ds;
+    if (det_scratch(&ds, (size_t)gx * d->cout, 1)) return 1;
     ::b200::launch_kernel(colsum_kernel, grid, 256, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(dy),
                                                       dbias, npix, d->cdy, d->dy_coff, d->cout,
-                                                      d->scale);
+                                                      d->scale, ds.part, ds.counters);
     B200_LAUNCH_CHECK();
   }
   if (!dw) return 0;
 
-  static bool attr_set = false;
   const int kSmemBytes = 200 * 1024;
-  if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
-  }
+  B200_ENSURE_SMEM(conv_wgrad_kernel, kSmemBytes);
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.tw = d->w_out > 8 ? 16 : (d->w_out > 4 ? 8 : 4);
@@ -330,6 +355,12 @@ extern "C" int b200_conv_wgrad(const b200_wgrad_desc* d, const void* x, const vo
   B200_REQUIRE(p.stages >= 2, "b200_conv_wgrad: smem");
   p.scale = d->scale;
   p.dw = dw;
+  p.ws = nullptr;
+  if (p.splits > 1) {
+    DetScratch ds;
+    if (det_scratch(&ds, (size_t)p.splits * p.taps * d->cout * d->cin, 0)) return 1;
+    p.ws = ds.part;
+  }
   {
     uint64_t dims[4] = {(uint64_t)(d->x_coff + d->cin), (uint64_t)d->w_in, (uint64_t)d->h_in,
                         (uint64_t)d->n};
@@ -352,6 +383,14 @@ extern "C" int b200_conv_wgrad(const b200_wgrad_desc* d, const void* x, const vo
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   ::b200::launch_kernel(conv_wgrad_kernel, grid, kThreads, smem, as_stream(stream), p);
   B200_LAUNCH_CHECK();
+  if (p.ws) {
+    const long long per = (long long)p.taps * d->cout * d->cin;
+    long long blocks = (per + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    ::b200::launch_kernel(wgrad_reduce_kernel, (int)blocks, 256, 0, as_stream(stream), (const float*)p.ws, dw, p.splits,
+                          p.taps, (int)d->cout, (int)d->cin, d->scale);
+    B200_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -43,7 +43,8 @@ __global__ void bn_reduce_kernel(const __nv_bfloat16* __restrict__ z,
                                  const __nv_bfloat16* __restrict__ da,
                                  const float* __restrict__ mean_invstd,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
-                                 float* __restrict__ sums, long long npix, int c, float slope) {
+                                 float* __restrict__ sums, long long npix, int c, float slope,
+                                 float* __restrict__ part, unsigned* __restrict__ counter) {
   pdl_trigger();
   pdl_wait();
   const int vec_per_pix = c / 8;
@@ -115,8 +116,11 @@ __global__ void bn_reduce_kernel(const __nv_bfloat16* __restrict__ z,
     const int ln = ch >> 3, j = (ch & 7) + 8 * which;
     float t = 0.f;
     for (int q = ln; q < 256; q += vec_per_pix) t += sh[j * 256 + q];
-    atomicAdd(&sums[k], t);
+    part[(size_t)blockIdx.x * 2 * c + k] = t;
   }
+  // deterministic grid reduction: the last block to arrive adds the per-block partials in block order
+  if (det_arrive_last(counter, gridDim.x))
+    det_sum_blocks(part, gridDim.x, 2 * c, sh, [&](int k, float t) { sums[k] = t; });
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, float* __restrict__ mean_invstd,
@@ -402,7 +406,7 @@ __device__ __forceinline__ void st_from_float(__nv_bfloat16* p, long long i, flo
 template <typename T>
 __global__ void l1_loss_kernel(const T* __restrict__ a, const T* __restrict__ b,
                                float* __restrict__ loss_out, T* __restrict__ grad_a, long long numel,
-                               float scale) {
+                               float scale, float* __restrict__ part, unsigned* __restrict__ counter) {
   pdl_trigger();
   pdl_wait();
   // scale = weight / numel
@@ -421,7 +425,16 @@ __global__ void l1_loss_kernel(const T* __restrict__ a, const T* __restrict__ b,
   if (w == 0) {
     s = l < (blockDim.x >> 5) ? red[l] : 0.f;
     s = warp_sum(s);
-    if (l == 0) atomicAdd(loss_out, s * scale);
+    if (l == 0) part[blockIdx.x] = s;
+  }
+  // deterministic grid reduction (block order) by the last block to arrive
+  if (det_arrive_last(counter, gridDim.x)) {
+    if (w == 0) {
+      float t = 0.f;
+      for (unsigned b = l; b < gridDim.x; b += 32) t += part[b];
+      t = warp_sum(t);
+      if (l == 0) *loss_out = t * scale;
+    }
   }
 }
 
@@ -483,10 +496,10 @@ __global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict_
 }
 
 // grid such that (grid*256) % vec_per_pix == 0 so each thread keeps one channel lane
-inline int bn_grid(long long npix, int c, int per_thread) {
+inline int bn_grid(long long npix, int c, int per_thread, int max_blocks = 148 * 8) {
   const int vpp = c / 8;
   long long total = (npix * vpp + per_thread - 1) / per_thread;
-  int g = grid_for(total, 256, 148 * 8);
+  int g = grid_for(total, 256, max_blocks);
   // 256 * g divisible by vpp: vpp is a power of two <= 64 for c in {64,128,256,512}; otherwise fix up
   while ((256LL * g) % vpp != 0) ++g;
   return g;
@@ -502,9 +515,11 @@ extern "C" {
 
 int b200_bn_stats(const void* z, float* stats, int64_t npix, int32_t c, b200_stream_t stream) {
   B200_REQUIRE(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "b200_bn_stats: c/8 must be a power of two <= 256 (c=%d)", c);
-  B200_CHECK_CUDA(cudaMemsetAsync(stats, 0, 2 * c * sizeof(float), as_stream(stream)));
-  ::b200::launch_kernel(bn_reduce_kernel<0>, bn_grid(npix, c, 4), 256, 16 * 256 * sizeof(float), as_stream(stream), 
-      (const bf16*)z, nullptr, nullptr, nullptr, nullptr, stats, npix, c, 0.f);
+  const int grid = bn_grid(npix, c, 4, 148 * 2);   // the last block adds the per-block partials: keep them few
+  DetScratch ds;
+  if (det_scratch(&ds, (size_t)grid * 2 * c, 1)) return 1;
+  ::b200::launch_kernel(bn_reduce_kernel<0>, grid, 256, 16 * 256 * sizeof(float), as_stream(stream), 
+      (const bf16*)z, nullptr, nullptr, nullptr, nullptr, stats, npix, c, 0.f, ds.part, ds.counters);
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -532,9 +547,11 @@ int b200_bn_bwd_reduce(const void* z, const void* da, const float* mean_invstd, 
                        const float* beta, float* sums, int64_t npix, int32_t c, float slope,
                        b200_stream_t stream) {
   B200_REQUIRE(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "b200_bn_bwd_reduce: c/8 must be a power of two <= 256 (c=%d)", c);
-  B200_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * c * sizeof(float), as_stream(stream)));
-  ::b200::launch_kernel(bn_reduce_kernel<1>, bn_grid(npix, c, 4), 256, 16 * 256 * sizeof(float), as_stream(stream), 
-      (const bf16*)z, (const bf16*)da, mean_invstd, gamma, beta, sums, npix, c, slope);
+  const int grid = bn_grid(npix, c, 4, 148 * 2);   // the last block adds the per-block partials: keep them few
+  DetScratch ds;
+  if (det_scratch(&ds, (size_t)grid * 2 * c, 1)) return 1;
+  ::b200::launch_kernel(bn_reduce_kernel<1>, grid, 256, 16 * 256 * sizeof(float), as_stream(stream), 
+      (const bf16*)z, (const bf16*)da, mean_invstd, gamma, beta, sums, npix, c, slope, ds.part, ds.counters);
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -608,18 +625,22 @@ int b200_pixel_unshuffle2(const void* dout, void* dz, int32_t n, int32_t h, int3
 
 int b200_l1_loss_f32(const float* a, const float* b, float* loss_out, float* grad_a, int64_t numel,
                      float weight, b200_stream_t stream) {
-  B200_CHECK_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), as_stream(stream)));
-  ::b200::launch_kernel(l1_loss_kernel<float>, grid_for(numel, 256, 148 * 4), 256, 0, as_stream(stream), 
-      a, b, loss_out, grad_a, numel, weight / (float)numel);
+  const int grid = grid_for(numel, 256, 148 * 4);
+  DetScratch ds;
+  if (det_scratch(&ds, (size_t)grid, 1)) return 1;
+  ::b200::launch_kernel(l1_loss_kernel<float>, grid, 256, 0, as_stream(stream), 
+      a, b, loss_out, grad_a, numel, weight / (float)numel, ds.part, ds.counters);
   B200_LAUNCH_CHECK();
   return 0;
 }
 
 int b200_l1_loss_bf16(const void* a, const void* b, float* loss_out, void* grad_a, int64_t numel,
                       float weight, b200_stream_t stream) {
-  B200_CHECK_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), as_stream(stream)));
-  ::b200::launch_kernel(l1_loss_kernel<bf16>, grid_for(numel, 256, 148 * 4), 256, 0, as_stream(stream), 
-      (const bf16*)a, (const bf16*)b, loss_out, (bf16*)grad_a, numel, weight / (float)numel);
+  const int grid = grid_for(numel, 256, 148 * 4);
+  DetScratch ds;
+  if (det_scratch(&ds, (size_t)grid, 1)) return 1;
+  ::b200::launch_kernel(l1_loss_kernel<bf16>, grid, 256, 0, as_stream(stream), 
+      (const bf16*)a, (const bf16*)b, loss_out, (bf16*)grad_a, numel, weight / (float)numel, ds.part, ds.counters);
   B200_LAUNCH_CHECK();
   return 0;
 }

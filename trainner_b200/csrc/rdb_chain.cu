@@ -1,0 +1,529 @@
+// Whole-trunk residual-dense-block chain in ONE persistent launch (sm_100a, tcgen05 + TMEM + TMA).
+//
+// A dense block is 5 stacked 3x3 convs where conv_k consumes [x, x1 .. x_{k-1}].  Computed conv by conv,
+// four of them have only 32 output channels and tcgen05.mma is shared-memory-operand bound at 40 % of the
+// tensor pipe (N = 32; profiles/r01_umma_pipe_probe.log).  Here a block is computed INPUT SLICE by input slice:
+//   stage j consumes the newest slice S_j (x for j = 0, then x1..x4) and adds its contribution to ALL convs
+//   that still need it:  D[:, 32j:192] += S_j (*) W_stage_j      (N = 192 - 32 j, K = 64 or 32 per tap)
+// and the fp32 partial sums of a 128-position tile (192 columns) stay in TMEM for the whole block.  After stage j
+// the 32 (last stage: 64) columns that just became complete are finished (bias / LeakyReLU or mask / residuals),
+// written to HBM (saved activation / gradient) and -- as bf16, already in the 128B-swizzled K-major layout --
+// straight back into the CTA's own shared-memory operand region: they ARE the next stage's A operand.
+// The output of stage 4 is the x slice of the NEXT block, so the whole trunk (69 blocks x 5 stages) runs in
+// one launch with the activations never leaving the SM except as stores.
+//
+// Each CTA owns TWO 128-position tiles of the flat (zero-bordered) position space, one from each half of the
+// image group (so the two tiles never depend on each other), with one MMA-issuing warp and four epilogue
+// warps per tile; the stage weights stream once per CTA through a TMA ring shared by both tiles.  While one
+// tile's finished slice is being turned around (TMEM -> registers -> smem, ~1 k cycles) the other tile's MMAs
+// keep the tensor pipe busy.
+//
+// Halo rows (the +-(w+3) positions a 3x3 tap reaches beyond the tile) belong to the neighbouring tiles = the
+// neighbouring CTAs.  They travel through L2 in "LL" form: every 16-byte store carries 8 bytes of data and two
+// copies of a 4-byte sequence flag (8-byte atomicity), the receiver polls the data itself -- no fence, no
+// separate flag round trip (the round-1 kernel rdb_persist.cu spent ~6.5 k cycles per stage on store -> fence
+// -> flag -> acquire -> TMA reload of the whole operand).  All CTAs are co-resident (cooperative launch).
+//
+// The gather-form input gradient of a block has exactly the same shape with the slices taken in reverse
+// (dO, dY4 .. dY1 -> d(x4) .. d(x)), so the backward trunk is the same kernel with flipped taps.
+//
+// Reference: ResidualDenseBlock_5C.forward + RRDB residuals (RRDBNet_arch.py:89-96,150-163), the ShortcutBlock
+// trunk (block.py:184-192) and their autograd input gradients.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int kThreads = 352;          // weights producer, 2 MMA issuers, 2 x 4 epilogue warps
+constexpr int kTileM = 128;
+constexpr int kNTotal = 192;
+constexpr int kBStages = 4;
+constexpr uint32_t kBStageBytes = 32 * 1024;   // one 64-channel tap tile (24 KB) or three 32-channel tap tiles (<= 30 KB)
+constexpr int kLLRowBytes = 256;       // 128 B of data (64 channels) in LL form
+constexpr int kMaxHalo = 131;          // w <= 128
+
+struct ChainParams {
+  CUtensorMap x_map;       // input of the first block: flat [P rows][>= 64 ch], box (64, box_rows)
+  CUtensorMap w_map[5];    // stage weights: 2-D [n_blocks * 9 * N_j rows][K_j], box (K_j, N_j)
+  const b200_chain_stage* table;   // [n_blocks][5]
+  int n_blocks;
+  int x_ch;                // channel offset of the first block's input slice
+  int Wp, HpWp, h, w, halo, nbox, box_rows;
+  uint32_t a_bytes, a_region_bytes;
+  int range_pos0[2], range_len[2], range_tiles[2];   // the two position ranges (halves of the image group)
+  int tap_sign;            // +1 forward taps, -1 input-gradient taps
+  uint8_t* ll;             // LL exchange buffers [range][tile][side][parity][halo rows][256 B]
+  uint32_t ll_tile_stride; // bytes per (range, tile)
+  const uint32_t* epoch;   // launch sequence number (bumped by a 1-thread kernel before this one)
+  int skew_cycles;         // tile 1 starts this many cycles after tile 0 (de-phases the two pipelines)
+  long long* dbg;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Operands of a stage epilogue that do not depend on the accumulator, requested BEFORE the wait on the MMAs.
+struct EpiPre {
+  uint4 lm[4], l1[4], l2[4];
+  float4 b[8];
+};
+
+__device__ __forceinline__ void prefetch32(const b200_chain_stage& e, EpiPre& q, int c0, long long m) {
+  const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(e.mask);
+  const __nv_bfloat16* res1 = reinterpret_cast<const __nv_bfloat16*>(e.res1);
+  const __nv_bfloat16* res2 = reinterpret_cast<const __nv_bfloat16*>(e.res2);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int c = c0 + g * 8;
+    if (mask) q.lm[g] = *reinterpret_cast<const uint4*>(mask + m * e.mask_c + e.mask_coff + c);
+    if (res1) q.l1[g] = *reinterpret_cast<const uint4*>(res1 + m * e.res1_c + e.res1_coff + c);
+    if (res2) q.l2[g] = *reinterpret_cast<const uint4*>(res2 + m * e.res2_c + e.res2_coff + c);
+    if (e.bias) {
+      q.b[2 * g] = __ldg(reinterpret_cast<const float4*>(e.bias + c));
+      q.b[2 * g + 1] = __ldg(reinterpret_cast<const float4*>(e.bias + c + 4));
+    }
+  }
+}
+
+// finish 32 accumulator columns of one row -> 4 packed 16-byte chunks
+__device__ __forceinline__ void finish32(const b200_chain_stage& e, const uint32_t* acc, const EpiPre& q, uint4* o) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
+    if (e.bias) {
+      const float4 b0 = q.b[2 * g], b1 = q.b[2 * g + 1];
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= e.alpha;
+    if (e.res1) {
+      float r[8];
+      unpack8(q.l1[g], r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(e.beta1, r[j], v[j]);
+    }
+    if (e.res2) {
+      float r[8];
+      unpack8(q.l2[g], r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(e.beta2, r[j], v[j]);
+    }
+    if (e.act) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * e.slope;
+    }
+    if (e.mask) {
+      float r[8];
+      unpack8(q.lm[g], r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = r[j] > 0.f ? v[j] : v[j] * e.mask_slope;
+    }
+    o[g] = pack8(v);
+  }
+}
+
+#define CDBG(slot) do { if (p.dbg && lane == 0) p.dbg[(long long)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+
+__global__ void __launch_bounds__(kThreads, 1)
+rdb_chain_kernel(const __grid_constant__ ChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem =
+      reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t b_full[kBStages], b_empty[kBStages], init_full[2], slice_ready[2], acc_ready[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int cta = blockIdx.x;
+  // tile `t` of this CTA = tile number `cta` of position range t; inactive when the range has fewer tiles
+  const bool active0 = cta < p.range_tiles[0], active1 = cta < p.range_tiles[1];
+  const int n_active = (active0 ? 1 : 0) + (active1 ? 1 : 0);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kBStages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], n_active);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&init_full[t], 1);
+      mbar_init(&slice_ready[t], 4);   // one arrival per epilogue warp of the tile
+      mbar_init(&acc_ready[t], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t b_ring_off = 2 * p.a_region_bytes;
+  const int n_stages_total = p.n_blocks * 5;
+  if (warp == 0) CDBG(0);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ producer: initial operand regions, then weights
+    if (elect_one()) {
+      tma_prefetch_desc(&p.x_map);
+      for (int j = 0; j < 5; ++j) tma_prefetch_desc(&p.w_map[j]);
+      for (int t = 0; t < 2; ++t) {
+        if (!(t == 0 ? active0 : active1)) continue;
+        const int row0 = p.range_pos0[t] + cta * kTileM - p.halo;
+        uint8_t* sa = smem + (size_t)t * p.a_region_bytes;
+        mbar_expect_tx(&init_full[t], p.a_bytes);
+        for (int bx = 0; bx < p.nbox; ++bx)
+          tma_load_2d(sa + (size_t)bx * p.box_rows * 128, &p.x_map, &init_full[t], p.x_ch, row0 + bx * p.box_rows);
+      }
+    }
+    __syncwarp();
+    if (n_active > 0) {
+      int bs = 0;
+      uint32_t bph = 0;
+      for (int blk = 0; blk < p.n_blocks; ++blk) {
+        for (int j = 0; j < 5; ++j) {
+          const int N = kNTotal - 32 * j;
+          const int tpb = (j == 0) ? 1 : 3;   // taps per weight slot
+          const uint32_t tap_bytes = (uint32_t)N * (j == 0 ? 128 : 64);
+          const int row_base = blk * 9 * N;
+          for (int t0 = 0; t0 < 9; t0 += tpb) {
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&b_full[bs], tap_bytes * tpb);
+              for (int q = 0; q < tpb; ++q)
+                tma_load_2d(smem + b_ring_off + (size_t)bs * kBStageBytes + (size_t)q * tap_bytes, &p.w_map[j],
+                            &b_full[bs], 0, row_base + (t0 + q) * N);
+            }
+            __syncwarp();
+            if (++bs == kBStages) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------------------ MMA issuer of tile (warp - 1)
+    const int tile = warp - 1;
+    const bool active = tile == 0 ? active0 : active1;
+    if (active) {
+      const uint64_t desc_hi = make_smem_desc(0, 16, 1024, LAYOUT_SW128, 0);
+      const uint64_t desc_b64 = make_smem_desc(0, 16, 512, LAYOUT_SW64, 0);   // 32-channel weight tiles: 64-byte rows
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t a_base = smem_base + tile * p.a_region_bytes + (uint32_t)p.halo * 128;
+      const uint32_t d_tile = tmem + tile * kNTotal;
+      uint32_t sh16[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) sh16[t] = (uint32_t)((p.tap_sign * ((t / 3 - 1) * p.Wp + (t % 3 - 1))) * 8);   // 128-B rows in 16-B units
+      if (tile == 1 && p.skew_cycles > 0) {
+        const long long t_go = clock64() + p.skew_cycles;
+        while (clock64() < t_go) {
+        }
+      }
+      int bs = 0;
+      uint32_t bph = 0, ready_ph = 0;
+      for (int s = 0; s < n_stages_total; ++s) {
+        const int j = s % 5;
+        const int N = kNTotal - 32 * j;
+        const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+        const uint32_t d_tmem = d_tile + 32 * j;
+        if (s == 0) {
+          mbar_wait(&init_full[tile], 0);
+        } else {
+          mbar_wait(&slice_ready[tile], ready_ph);
+          ready_ph ^= 1;
+        }
+        tc_fence_after();
+        if (s < 16 && tile == 0) CDBG(2 + 3 * s);   // operand slice ready
+        const int tpb = (j == 0) ? 1 : 3;
+        const uint32_t tap16 = ((uint32_t)N * (j == 0 ? 128 : 64)) >> 4;
+        const uint32_t a16 = a_base >> 4;
+        for (int t0 = 0; t0 < 9; t0 += tpb) {
+          mbar_wait(&b_full[bs], bph);
+          tc_fence_after();
+          const uint32_t b16 = (smem_base + b_ring_off + bs * kBStageBytes) >> 4;
+          if (elect_one()) {
+            if (j == 0) {
+              const uint32_t at = a16 + sh16[t0];
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(d_tmem, desc_hi | (uint64_t)((at + 2 * k) & 0x3FFF), desc_hi | (uint64_t)((b16 + 2 * k) & 0x3FFF), idesc,
+                         (t0 | k) != 0);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 3; ++q) {
+                const uint32_t at = a16 + sh16[t0 + q], bt = b16 + q * tap16;
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                  umma_f16(d_tmem, desc_hi | (uint64_t)((at + 2 * k) & 0x3FFF), desc_b64 | (uint64_t)((bt + 2 * k) & 0x3FFF), idesc,
+                           1u);
+              }
+            }
+            umma_commit(&b_empty[bs]);
+            if (t0 + tpb >= 9) umma_commit(&acc_ready[tile]);
+          }
+          __syncwarp();
+          if (++bs == kBStages) {
+            bs = 0;
+            bph ^= 1;
+          }
+        }
+        if (s < 16 && tile == 0) CDBG(3 + 3 * s);   // stage MMAs issued
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps: 3..6 -> tile 0, 7..10 -> tile 1
+    const int tile = (warp - 3) >> 2;
+    const bool active = tile == 0 ? active0 : active1;
+    if (active) {
+      const int quad = warp & 3;
+      const int r = quad * 32 + lane;                       // row of the tile == TMEM lane
+      const int et = ((warp - 3) & 3) * 32 + lane;          // 0..127: index among the tile's epilogue threads
+      const int lpos = cta * kTileM + r;                    // position within the range
+      const long long m = (long long)p.range_pos0[tile] + lpos;
+      const int rem = (int)(m % p.HpWp);
+      const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
+      const bool valid = lpos < p.range_len[tile] && yp >= 1 && yp <= p.h && xp >= 1 && xp <= p.w;
+      const bool has_up = cta > 0, has_dn = cta + 1 < p.range_tiles[tile];
+      const uint32_t t_row = tmem + ((uint32_t)(quad * 32) << 16) + tile * kNTotal;
+      const uint32_t region = smem_u32(smem) + tile * p.a_region_bytes;
+      const uint32_t own_row = (uint32_t)(p.halo + r);
+      const uint32_t own_addr = region + own_row * 128;
+      const uint32_t own_xor = own_row & 7;
+      uint8_t* ll_me = p.ll + ((size_t)tile * gridDim.x + cta) * p.ll_tile_stride;
+      uint8_t* ll_up = ll_me - p.ll_tile_stride;   // receive buffers of tile - 1 / tile + 1 of the same range
+      uint8_t* ll_dn = ll_me + p.ll_tile_stride;
+      const uint32_t side_bytes = (uint32_t)p.halo * kLLRowBytes;   // one (side, parity) buffer
+      const uint32_t flag0 = (*p.epoch) << 12;
+      uint32_t acc_ph = 0;
+      for (int s = 0; s < n_stages_total; ++s) {
+        const int j = s % 5;
+        const b200_chain_stage e = p.table[s];
+        const int nch = (j == 4) ? 8 : 4;              // 16-byte chunks of the finished slice (64 or 32 channels)
+        const uint32_t flag = flag0 + (uint32_t)s + 1u;
+        const int par = s & 1;
+        EpiPre q;
+        if (valid) prefetch32(e, q, 0, m);
+        mbar_wait(&acc_ready[tile], acc_ph);
+        acc_ph ^= 1;
+        tc_fence_after();
+        if (s < 16 && warp == 3) CDBG(4 + 3 * s);   // stage MMAs complete
+        __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(e.out);
+        for (int c0 = 0; c0 < nch * 8; c0 += 32) {
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(t_row + 32 * j + c0, acc);
+          if (c0 > 0 && valid) prefetch32(e, q, c0, m);
+          tmem_ld_wait();
+          uint4 o[4];
+          if (valid) {
+            finish32(e, acc, q, o);
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) o[g] = make_uint4(0, 0, 0, 0);   // border / out-of-range positions stay zero
+          }
+          const int cb = c0 >> 3;   // first chunk index
+          // (1) own rows of the next operand slice, 128B-swizzled K-major
+#pragma unroll
+          for (int g = 0; g < 4; ++g) st_shared_v4(own_addr + ((uint32_t)((cb + g) ^ own_xor) << 4), o[g]);
+          // (2) halo rows for the neighbouring tiles (LL: data + flag in every 8 bytes)
+          if (has_up && r < p.halo) {
+            uint8_t* dst = ll_up + (1 * 2 + par) * side_bytes + (size_t)r * kLLRowBytes + cb * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              st_global_v4(dst + g * 32, o[g].x, flag, o[g].y, flag);
+              st_global_v4(dst + g * 32 + 16, o[g].z, flag, o[g].w, flag);
+            }
+          }
+          if (has_dn && r >= kTileM - p.halo) {
+            uint8_t* dst = ll_dn + (0 * 2 + par) * side_bytes + (size_t)(r - (kTileM - p.halo)) * kLLRowBytes + cb * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              st_global_v4(dst + g * 32, o[g].x, flag, o[g].y, flag);
+              st_global_v4(dst + g * 32 + 16, o[g].z, flag, o[g].w, flag);
+            }
+          }
+          // (3) saved activation / gradient in HBM
+          if (valid && outp) {
+            uint4* dst = reinterpret_cast<uint4*>(outp + m * e.out_c + e.out_coff + c0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) dst[g] = o[g];
+          }
+        }
+        tc_fence_before();
+        // (4) halo rows of the finished slice from the neighbouring tiles -> own operand region
+        if (s + 1 < n_stages_total) {
+          const int per_side = p.halo * nch;
+          for (int i = et; i < 2 * per_side; i += 128) {
+            const int side = i >= per_side ? 1 : 0;
+            if (side == 0 ? !has_up : !has_dn) continue;
+            const int k = i - side * per_side;
+            const int row = k / nch, ch = k - row * nch;
+            const uint8_t* src = ll_me + (side * 2 + par) * side_bytes + (size_t)row * kLLRowBytes + ch * 32;
+            uint4 a, b;
+            do {
+              a = ld_volatile_v4(src);
+              b = ld_volatile_v4(src + 16);
+            } while (a.y != flag || a.w != flag || b.y != flag || b.w != flag);
+            const uint32_t R = side == 0 ? (uint32_t)row : (uint32_t)(p.halo + kTileM + row);
+            st_shared_v4(region + R * 128 + ((uint32_t)(ch ^ (R & 7)) << 4), make_uint4(a.x, a.z, b.x, b.z));
+          }
+          fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&slice_ready[tile]);
+        }
+        if (s < 16 && warp == 3) CDBG(5 + 3 * s);   // slice turned around
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) CDBG(1);
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+__global__ void chain_epoch_bump_kernel(uint32_t* epoch) {
+  pdl_trigger();
+  pdl_wait();
+  *epoch = (*epoch + 1u) & 0xFFFFFu;   // flag = (epoch << 12) + stage + 1 stays below 2^32
+  if (*epoch == 0u) *epoch = 1u;
+}
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_rdb_chain_geometry(int32_t n, int32_t h, int32_t w, int32_t* n_cta, int64_t* ll_bytes) {
+  const int Hp = h + 2, Wp = w + 2;
+  const int n0 = (n + 1) / 2;
+  const long long len0 = (long long)n0 * Hp * Wp;
+  const int tiles = (int)((len0 + kTileM - 1) / kTileM);
+  if (n_cta) *n_cta = tiles;
+  const int halo = Wp + 1;
+  if (ll_bytes) *ll_bytes = (int64_t)2 * tiles * 4 * halo * kLLRowBytes;
+  return 0;
+}
+
+// One launch = a chain of n_blocks dense blocks (forward, or gather-form input gradient when flip_taps) over
+// the n images starting at image `img0` of the flat tensors.  table_dev: [n_blocks][5] stage descriptors
+// (device memory); w_stage[j]: packed stage weights [n_blocks][9][192-32j][K_j] bf16 (K_0 = 64, else 32).
+extern "C" int b200_rdb_chain(const b200_chain_desc* d, const void* x0, const void* const* w_stage,
+                              const b200_chain_stage* table_dev, void* ll_buf, int64_t ll_bytes,
+                              uint32_t* epoch_dev, b200_stream_t stream) {
+  B200_REQUIRE(d && x0 && w_stage && table_dev && ll_buf && epoch_dev, "b200_rdb_chain: null argument");
+  B200_REQUIRE(d->n >= 1 && d->n_blocks >= 1 && d->w + 3 <= kMaxHalo, "b200_rdb_chain: bad geometry (w <= 128)");
+  ChainParams p;
+  memset(&p, 0, sizeof(p));
+  p.h = d->h; p.w = d->w;
+  p.Wp = d->w + 2;
+  const int Hp = d->h + 2;
+  p.HpWp = Hp * p.Wp;
+  p.halo = p.Wp + 1;
+  const int region = kTileM + 2 * p.halo;
+  p.nbox = (region + 255) / 256;
+  p.box_rows = (((region + p.nbox - 1) / p.nbox) + 7) & ~7;
+  p.a_bytes = (uint32_t)p.nbox * p.box_rows * 128;
+  p.a_region_bytes = (p.a_bytes + 1023) & ~1023u;
+  const int kSmemBytes = (int)(2 * p.a_region_bytes + kBStages * kBStageBytes + 1024);
+  B200_REQUIRE(kSmemBytes <= 227 * 1024, "b200_rdb_chain: image too wide for the shared-memory operand regions (w=%d)", d->w);
+  B200_ENSURE_SMEM(rdb_chain_kernel, kSmemBytes);
+  const int n0 = (d->n + 1) / 2, n1 = d->n - n0;
+  const long long P_total = (long long)d->n_total * p.HpWp;
+  p.range_pos0[0] = d->img0 * p.HpWp;
+  p.range_len[0] = n0 * p.HpWp;
+  p.range_pos0[1] = (d->img0 + n0) * p.HpWp;
+  p.range_len[1] = n1 * p.HpWp;
+  for (int t = 0; t < 2; ++t) p.range_tiles[t] = (p.range_len[t] + kTileM - 1) / kTileM;
+  const int n_cta = p.range_tiles[0];
+  const int sms = sm_count();
+  B200_REQUIRE(n_cta <= sms, "b200_rdb_chain: %d tile pairs exceed the %d SMs (split the batch)", n_cta, sms);
+  int n_cta_chk;
+  int64_t need;
+  b200_rdb_chain_geometry(d->n, d->h, d->w, &n_cta_chk, &need);
+  B200_REQUIRE(ll_bytes >= need, "b200_rdb_chain: exchange buffer of %lld bytes needed", (long long)need);
+  p.ll = reinterpret_cast<uint8_t*>(ll_buf);
+  p.ll_tile_stride = (uint32_t)(4 * p.halo * kLLRowBytes);
+  p.epoch = epoch_dev;
+  p.table = table_dev;
+  p.n_blocks = d->n_blocks;
+  p.x_ch = d->x_coff;
+  p.tap_sign = d->flip_taps ? -1 : 1;
+  {
+    static int skew = -1;
+    if (skew < 0) {
+      const char* e = getenv("B200_CHAIN_SKEW");
+      skew = e ? atoi(e) : 1500;
+    }
+    p.skew_cycles = skew;
+  }
+  {
+    const char* e = getenv("B200_CHAIN_DBG_PTR");
+    p.dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)(d->x_coff + 64), (uint64_t)P_total};
+    uint64_t strides[1] = {(uint64_t)d->cx * 2};
+    uint32_t box[2] = {64, (uint32_t)p.box_rows};
+    if (make_tensor_map(&p.x_map, x0, 2, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  for (int j = 0; j < 5; ++j) {
+    B200_REQUIRE(w_stage[j], "b200_rdb_chain: null stage weights");
+    const int N = kNTotal - 32 * j;
+    const uint64_t kc = (j == 0) ? 64 : 32;
+    uint64_t dims[2] = {kc, (uint64_t)d->n_blocks * 9 * N};
+    uint64_t strides[1] = {kc * 2};
+    uint32_t box[2] = {(uint32_t)kc, (uint32_t)N};
+    if (make_tensor_map(&p.w_map[j], w_stage[j], 2, dims, strides, box, nullptr,
+                        kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))
+      return 1;
+  }
+  ::b200::launch_kernel(chain_epoch_bump_kernel, 1, 1, 0, as_stream(stream), epoch_dev);
+  B200_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_cta);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: the neighbour exchange cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rdb_chain_kernel, p));
+  g_launches.fetch_add(1);
+  return 0;
+}

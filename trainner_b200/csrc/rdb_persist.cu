@@ -338,13 +338,8 @@ using namespace b200;
 extern "C" int b200_rdb_persist(const b200_rdb_desc* d, int* flags, int32_t flag_base,
                                 b200_stream_t stream) {
   B200_REQUIRE(d && flags, "b200_rdb_persist: null argument");
-  static bool attr_set = false;
   const int kSmemBytes = 202 * 1024;
-  if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(rdb_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kSmemBytes));
-    attr_set = true;
-  }
+  B200_ENSURE_SMEM(rdb_persist_kernel, kSmemBytes);
   RdbParams p;
   memset(&p, 0, sizeof(p));
   p.h = d->h; p.w = d->w;

@@ -177,7 +177,8 @@ template <int CS>
 __global__ void __launch_bounds__(256)
 thin_wgrad_kernel(const float* __restrict__ thin, const __nv_bfloat16* __restrict__ wide,
                   float* __restrict__ dw, float* __restrict__ dbias_wide, int n, int h, int w,
-                  int cw, int cwide_buf, int wide_coff, int wide_is_out) {
+                  int cw, int cwide_buf, int wide_coff, int wide_is_out, float* __restrict__ part,
+                  unsigned* __restrict__ counters) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float rows[];  // [CS][3][w + 2]
@@ -240,22 +241,31 @@ thin_wgrad_kernel(const float* __restrict__ thin, const __nv_bfloat16* __restric
       }
     }
   }
-  // reduce the 4 pixel subsets, then one atomic per (j, i, t)
+  // reduce the 4 pixel subsets into this block's partial row [64 lanes][CS*9 + 1]; the last block of the
+  // channel group (blockIdx.y) to arrive adds the rows of all blocks in block order (deterministic)
+  constexpr int NC1 = CS * 9 + 1;
+  float* mine = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 * NC1;
 #pragma unroll
-  for (int k = 0; k < CS * 9 + 1; ++k) {
+  for (int k = 0; k < NC1; ++k) {
     __syncthreads();
     red[sub][lane_c] = (k < CS * 9) ? acc[k] : bsum;
     __syncthreads();
-    if (sub == 0 && j < cw) {
-      const float s = red[0][lane_c] + red[1][lane_c] + red[2][lane_c] + red[3][lane_c];
+    if (sub == 0) mine[lane_c * NC1 + k] = red[0][lane_c] + red[1][lane_c] + red[2][lane_c] + red[3][lane_c];
+  }
+  if (det_arrive_last(counters + blockIdx.y, gridDim.x)) {
+    __shared__ float shs[256];
+    det_sum_blocks(part + (size_t)blockIdx.y * gridDim.x * 64 * NC1, gridDim.x, 64 * NC1, shs, [&](int i, float sv) {
+      const int m = i / NC1, k = i % NC1;
+      const int jj = blockIdx.y * 64 + m;
+      if (jj >= cw) return;
       if (k < CS * 9) {
         const int ci = k / 9, t = k % 9;
-        const size_t idx = wide_is_out ? ((size_t)j * CS + ci) * 9 + t : ((size_t)ci * cw + j) * 9 + t;
-        atomicAdd(dw + idx, s);
+        const size_t idx = wide_is_out ? ((size_t)jj * CS + ci) * 9 + t : ((size_t)ci * cw + jj) * 9 + t;
+        dw[idx] += sv;
       } else if (dbias_wide) {
-        atomicAdd(dbias_wide + j, s);
+        dbias_wide[jj] += sv;
       }
-    }
+    });
   }
 }
 
@@ -504,7 +514,8 @@ template <int CS>
 __global__ void __launch_bounds__(256)
 thin_wgrad_mma_kernel(const float* __restrict__ thin, const __nv_bfloat16* __restrict__ wide,
                       float* __restrict__ dw, float* __restrict__ dbias_wide, int n, int h, int w, int w16,
-                      int cw, int cwide_buf, int wide_coff, int wide_is_out) {
+                      int cw, int cwide_buf, int wide_coff, int wide_is_out, float* __restrict__ part,
+                      unsigned* __restrict__ counters) {
   pdl_trigger();
   pdl_wait();
   constexpr int NC = CS * 9 + 1;          // used columns (the last one is the ones column)
@@ -596,23 +607,28 @@ thin_wgrad_mma_kernel(const float* __restrict__ thin, const __nv_bfloat16* __res
     }
     __syncthreads();
   }
-  for (int i = tid; i < 64 * NC; i += 256) {
-    const int m = i / NC, nn = i % NC;
-    const int j = jbase + m;
-    if (j >= cw) continue;
-    const float s = red[m * RS + nn];
-    if (nn < CS * 9) {
-      const int ci = nn / 9, tp = nn % 9;
-      const size_t idx = wide_is_out ? ((size_t)j * CS + ci) * 9 + tp : ((size_t)ci * cw + j) * 9 + tp;
-      atomicAdd(dw + idx, s);
-    } else if (dbias_wide) {
-      atomicAdd(dbias_wide + j, s);
-    }
+  // this block's partial [64][NC] -> scratch; the last block of the channel group adds all blocks in block order
+  float* mine = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 * NC;
+  for (int i = tid; i < 64 * NC; i += 256) mine[i] = red[(i / NC) * RS + (i % NC)];
+  if (det_arrive_last(counters + blockIdx.y, gridDim.x)) {
+    __shared__ float shs[256];
+    det_sum_blocks(part + (size_t)blockIdx.y * gridDim.x * 64 * NC, gridDim.x, 64 * NC, shs, [&](int i, float sv) {
+      const int m = i / NC, nn = i % NC;
+      const int j = jbase + m;
+      if (j >= cw) return;
+      if (nn < CS * 9) {
+        const int ci = nn / 9, tp = nn % 9;
+        const size_t idx = wide_is_out ? ((size_t)j * CS + ci) * 9 + tp : ((size_t)ci * cw + j) * 9 + tp;
+        dw[idx] += sv;
+      } else if (dbias_wide) {
+        dbias_wide[j] += sv;
+      }
+    });
   }
 }
 
 __global__ void plane_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int n, int c,
-                                 long long hw) {
+                                 long long hw, float* __restrict__ part, unsigned* __restrict__ counters) {
   pdl_trigger();
   pdl_wait();
   const int ch = blockIdx.y;
@@ -631,7 +647,12 @@ __global__ void plane_sum_kernel(const float* __restrict__ x, float* __restrict_
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
-    atomicAdd(out + ch, t);
+    part[ch * gridDim.x + blockIdx.x] = t;
+  }
+  if (det_arrive_last(counters + ch, gridDim.x) && threadIdx.x == 0) {
+    float t = 0.f;
+    for (unsigned b = 0; b < gridDim.x; ++b) t += part[ch * gridDim.x + b];
+    out[ch] += t;
   }
 }
 
@@ -731,12 +752,16 @@ int b200_conv3x3_thin_wgrad(const float* thin, const void* wide, float* dw, floa
   B200_REQUIRE(cs >= 1 && cs <= kMaxThin, "thin_wgrad: thin channels %d not in 1..4", cs);
   int gx = n * h < 2 * sm_count() ? n * h : 2 * sm_count();
   dim3 grid(gx, (cw + 63) / 64);
+  // deterministic cross-block reduction: per-block partials [grid.y][grid.x][64][cs*9+1] in the library scratch;
+  // the plane sums (launched after, stream-ordered) reuse the front of the same arena
+  DetScratch ds;
+  if (det_scratch(&ds, (size_t)grid.x * grid.y * 64 * (cs * 9 + 1) + 32 * 4, (int)grid.y + 8)) return 1;
   const int w16 = (w + 15) / 16 * 16;
   const size_t msm = (size_t)w16 * 128 + (size_t)cs * 3 * (w16 + 2) * sizeof(float);
   if (cw % 64 == 0 && cwide_buf % 8 == 0 && wide_coff % 8 == 0 && msm <= 48 * 1024 && msm >= 64 * 41 * 4) {
 #define LAUNCH_WGM(CS)                                                              \
   ::b200::launch_kernel(thin_wgrad_mma_kernel<CS>, grid, 256, msm, as_stream(stream),                  \
-      thin, (const bf16*)wide, dw, dbias_wide, n, h, w, w16, cw, cwide_buf, wide_coff, wide_is_out)
+      thin, (const bf16*)wide, dw, dbias_wide, n, h, w, w16, cw, cwide_buf, wide_coff, wide_is_out, ds.part, ds.counters)
     switch (cs) {
       case 1: LAUNCH_WGM(1); break;
       case 2: LAUNCH_WGM(2); break;
@@ -747,7 +772,7 @@ int b200_conv3x3_thin_wgrad(const float* thin, const void* wide, float* dw, floa
     B200_LAUNCH_CHECK();
     if (dbias_thin) {
       dim3 g2(32, cs);
-      ::b200::launch_kernel(plane_sum_kernel, g2, 256, 0, as_stream(stream), thin, dbias_thin, n, cs, (long long)h * w);
+      ::b200::launch_kernel(plane_sum_kernel, g2, 256, 0, as_stream(stream), thin, dbias_thin, n, cs, (long long)h * w, ds.part, ds.counters);
       B200_LAUNCH_CHECK();
     }
     return 0;
@@ -756,7 +781,7 @@ int b200_conv3x3_thin_wgrad(const float* thin, const void* wide, float* dw, floa
   B200_REQUIRE(smem <= 48 * 1024, "thin_wgrad: row too wide");
 #define LAUNCH_WG(CS)                                                               \
   ::b200::launch_kernel(thin_wgrad_kernel<CS>, grid, 256, smem, as_stream(stream),                     \
-      thin, (const bf16*)wide, dw, dbias_wide, n, h, w, cw, cwide_buf, wide_coff, wide_is_out)
+      thin, (const bf16*)wide, dw, dbias_wide, n, h, w, cw, cwide_buf, wide_coff, wide_is_out, ds.part, ds.counters)
   switch (cs) {
     case 1: LAUNCH_WG(1); break;
     case 2: LAUNCH_WG(2); break;
@@ -767,7 +792,7 @@ int b200_conv3x3_thin_wgrad(const float* thin, const void* wide, float* dw, floa
   B200_LAUNCH_CHECK();
   if (dbias_thin) {
     dim3 g2(32, cs);
-    ::b200::launch_kernel(plane_sum_kernel, g2, 256, 0, as_stream(stream), thin, dbias_thin, n, cs, (long long)h * w);
+    ::b200::launch_kernel(plane_sum_kernel, g2, 256, 0, as_stream(stream), thin, dbias_thin, n, cs, (long long)h * w, ds.part, ds.counters);
     B200_LAUNCH_CHECK();
   }
   return 0;

@@ -40,10 +40,11 @@ struct RdbItemParams {
   int n_rdb, P, Wp, k_steps, total_items;
   int nf, gc;
   int k_split, k_per;   // positions are split into k_split slices of k_per k-steps (see the host entry)
+  float* ws;            // [k_split][n_rdb][kSlabFloats] partial sums (nullptr when k_split == 1)
 };
 
 __device__ __forceinline__ void item_decode(const RdbItemParams& p, int item, int& r, int& dy, int& type,
-                                            int& ks0, int& ks1) {
+                                            int& ks0, int& ks1, int* slice_out = nullptr) {
   // heaviest type first so that the static round-robin schedule balances; the 9 * k_split items of one
   // RDB are adjacent so that the CTAs running at any moment share the same two or three RDBs' tensors
   type = item % 3;
@@ -54,6 +55,14 @@ __device__ __forceinline__ void item_decode(const RdbItemParams& p, int item, in
   r = q / p.k_split;
   ks0 = slice * p.k_per;
   ks1 = ks0 + p.k_per < p.k_steps ? ks0 + p.k_per : p.k_steps;
+  if (slice_out) *slice_out = slice;
+}
+
+// tap-major slab of one RDB in the split workspace: conv k at slab_off(k), element ((tap * cout_k + co) * cin_k + ci)
+constexpr int kSlabFloats = 9 * (32 * 64 + 32 * 96 + 32 * 128 + 32 * 160 + 64 * 192);   // 239616 (nf = 64, gc = 32)
+__host__ __device__ __forceinline__ int slab_off(int k, int nf, int gc) {
+  // 9 * gc * sum_{k' < k} (nf + k' gc)
+  return 9 * gc * (k * nf + gc * (k * (k - 1) / 2));
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -188,8 +197,8 @@ wgrad_rdb_kernel(const __grid_constant__ RdbItemParams p) {
     uint32_t acc_phase = 0;
     const int nf = p.nf, gc = p.gc;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      int r, dy, type, ks0, ks1;
-      item_decode(p, item, r, dy, type, ks0, ks1);
+      int r, dy, type, ks0, ks1, slice;
+      item_decode(p, item, r, dy, type, ks0, ks1, &slice);
       const b200_wgrad_rdb_entry e = p.rdbs[r];
       const int N = (type == 0) ? 128 : 64;
       mbar_wait(&tfull_bar, acc_phase);
@@ -198,36 +207,37 @@ wgrad_rdb_kernel(const __grid_constant__ RdbItemParams p) {
       for (int t = 0; t < 3; ++t) {
         const int tap = (dy + 1) * 3 + t;
         for (int c0 = 0; c0 < N; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(t_row + t * N + c0, v);
+          uint32_t v16[16];
+          tmem_ld_32x32b_x16(t_row + t * N + c0, v16);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int col = c0 + j;
-            float* dst = nullptr;
-            float scale = 1.f;
-            if (type == 0) {            // row = ci < 128 ; col -> conv k = col/gc + 1, co = col % gc
-              const int k = col / gc, co = col - k * gc;
-              const int cin_k = nf + k * gc;
-              if (row < cin_k) dst = e.dw[k] + ((size_t)co * cin_k + row) * 9 + tap;
+            // element (conv k, co, ci) of this tap; no atomics: it is owned by exactly one item per position slice
+            int k = -1, co = 0, ci = 0;
+            if (type == 0) {            // row = ci < 128 ; col -> conv k = col/gc, co = col % gc
+              k = col / gc;
+              co = col - k * gc;
+              ci = row;
+              if (row >= nf + k * gc) k = -1;
             } else if (type == 1) {     // conv5: ci = row < 128, co = col
-              const int cin5 = nf + 4 * gc;
-              dst = e.dw[4] + ((size_t)col * cin5 + row) * 9 + tap;
-              scale = e.scale5;
+              k = 4; co = col; ci = row;
             } else {                    // row = co' in [dY3 | dY4 | dO], col -> ci = 128 + col
-              const int ci = 2 * nf + col;   // nf = 64: X atom 2 starts at channel 128
-              if (row >= 2 * gc) {           // dO -> conv5
-                const int cin5 = nf + 4 * gc;
-                dst = e.dw[4] + ((size_t)(row - 2 * gc) * cin5 + ci) * 9 + tap;
-                scale = e.scale5;
-              } else if (row >= gc) {        // dY4 -> conv4 (cin 160): ci < 160
-                const int cin4 = nf + 3 * gc;
-                if (ci < cin4) dst = e.dw[3] + ((size_t)(row - gc) * cin4 + ci) * 9 + tap;
-              }                              // dY3 -> conv3 has only 128 inputs: nothing here
+              ci = 2 * nf + col;        // nf = 64: X atom 2 starts at channel 128
+              if (row >= 2 * gc) {      // dO -> conv5
+                k = 4; co = row - 2 * gc;
+              } else if (row >= gc && ci < nf + 3 * gc) {   // dY4 -> conv4 (cin 160)
+                k = 3; co = row - gc;
+              }                         // dY3 -> conv3 has only 128 inputs: nothing here
             }
-            if (dst) {
-              if (p.k_split > 1) atomicAdd(dst, scale * __uint_as_float(v[j]));   // slices of one item race
-              else *dst += scale * __uint_as_float(v[j]);
+            if (k >= 0) {
+              const int cin_k = nf + k * gc, cout_k = (k == 4) ? nf : gc;
+              const float v = __uint_as_float(v16[j]);
+              if (p.ws) {   // tap-major slab of this slice: lanes = consecutive ci (types 0, 1) / 16 consecutive ci per thread (type 2)
+                p.ws[((size_t)slice * p.n_rdb + r) * kSlabFloats + slab_off(k, nf, gc) + ((size_t)tap * cout_k + co) * cin_k + ci] = v;
+              } else {
+                e.dw[k][((size_t)co * cin_k + ci) * 9 + tap] += (k == 4 ? e.scale5 : 1.f) * v;
+              }
             }
           }
         }
@@ -243,12 +253,38 @@ wgrad_rdb_kernel(const __grid_constant__ RdbItemParams p) {
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-__global__ void __launch_bounds__(256) colsum_multi_kernel(const b200_colsum_entry* __restrict__ table) {
+// Second pass: dW_k (OIHW) += scale_k * sum over the position slices, in slice order (deterministic).
+__global__ void __launch_bounds__(256) wgrad_rdb_reduce_kernel(const float* __restrict__ ws,
+                                                               const b200_wgrad_rdb_entry* __restrict__ rdbs,
+                                                               int n_rdb, int k_split, int nf, int gc) {
+  pdl_trigger();
+  pdl_wait();
+  const int r = blockIdx.y;
+  const b200_wgrad_rdb_entry e = rdbs[r];
+  const size_t slice_stride = (size_t)n_rdb * kSlabFloats;
+  const float* base = ws + (size_t)r * kSlabFloats;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kSlabFloats; i += gridDim.x * blockDim.x) {
+    int k = 4;
+    while (i < slab_off(k, nf, gc)) --k;
+    const int cin_k = nf + k * gc, cout_k = (k == 4) ? nf : gc;
+    const int o = i - slab_off(k, nf, gc);
+    const int ci = o % cin_k, q = o / cin_k;
+    const int co = q % cout_k, tap = q / cout_k;
+    float s = 0.f;
+    for (int sl = 0; sl < k_split; ++sl) s += base[(size_t)sl * slice_stride + i];
+    e.dw[k][((size_t)co * cin_k + ci) * 9 + tap] += (k == 4 ? e.scale5 : 1.f) * s;
+  }
+}
+
+__global__ void __launch_bounds__(256) colsum_multi_kernel(const b200_colsum_entry* __restrict__ table,
+                                                           float* __restrict__ part, unsigned* __restrict__ counters,
+                                                           int c_max) {
   pdl_trigger();
   pdl_wait();
   __shared__ float red[256 * 8];
   const b200_colsum_entry e = table[blockIdx.y];
-  colsum_vec(reinterpret_cast<const __nv_bfloat16*>(e.src), e.npix, e.pitch, e.coff, e.c, e.scale, e.dst, red);
+  colsum_vec(reinterpret_cast<const __nv_bfloat16*>(e.src), e.npix, e.pitch, e.coff, e.c, e.scale, e.dst, red,
+             part + (size_t)blockIdx.y * gridDim.x * c_max, counters + blockIdx.y);
 }
 
 }  // namespace
@@ -259,9 +295,12 @@ using namespace b200;
 extern "C" int b200_colsum_multi(const b200_colsum_entry* table_dev, int32_t count, b200_stream_t stream) {
   if (count <= 0) return 0;
   B200_REQUIRE(table_dev, "b200_colsum_multi: null table");
-  // entries must have c % 8 == 0, c <= 2048, pitch % 8 == 0, coff % 8 == 0 (16-byte vector loads)
+  // entries must have c % 8 == 0, c <= c_max = 256, pitch % 8 == 0, coff % 8 == 0 (16-byte vector loads)
+  const int c_max = 256;
   dim3 grid(32, count);
-  ::b200::launch_kernel(colsum_multi_kernel, grid, 256, 0, as_stream(stream), table_dev);
+  DetScratch ds;
+  if (det_scratch(&ds, (size_t)count * 32 * c_max, count)) return 1;
+  ::b200::launch_kernel(colsum_multi_kernel, grid, 256, 0, as_stream(stream), table_dev, ds.part, ds.counters, c_max);
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -287,17 +326,40 @@ extern "C" int b200_wgrad_rdb_make_maps(void* maps_host, int32_t n_rdb, const vo
   return 0;
 }
 
+namespace {
+// Split-K for L2 locality, not for parallelism: with one item per (rdb, kernel row, type) the 148 CTAs
+// would stream 16 different RDBs (53 MB of X/dY each) at once and every operand byte would come from
+// HBM (18.6 GB per launch at config 2).  With S slices the CTAs in flight cover 16/S RDBs.  Each slice
+// writes its own tap-major slab of the caller's workspace with plain coalesced stores and a second kernel adds
+// the slabs in slice order: deterministic (round 1 used fp32 atomics: S=1 3.76 ms, S=4 3.41 ms, S=8 4.32 ms
+// because of the exposed atomic epilogue; operand phase alone 2.55 ms for S >= 4).
+void rdb_split(int k_steps, int* k_split, int* k_per) {
+  static int ksplit_env = -1;
+  if (ksplit_env < 0) {
+    const char* e = getenv("B200_WGRAD_RDB_KSPLIT");
+    ksplit_env = e ? atoi(e) : 8;
+    if (ksplit_env < 1) ksplit_env = 1;
+  }
+  int s = ksplit_env < k_steps ? ksplit_env : 1;
+  *k_per = (k_steps + s - 1) / s;
+  *k_split = (k_steps + *k_per - 1) / *k_per;   // no empty slices
+}
+}  // namespace
+
+extern "C" int64_t b200_wgrad_rdb_ws_bytes(int32_t n_rdb, int32_t n, int32_t h, int32_t w) {
+  const long long P = (long long)n * (h + 2) * (w + 2);
+  int k_split, k_per;
+  rdb_split((int)((P + 127) / 128), &k_split, &k_per);
+  return k_split > 1 ? (int64_t)k_split * n_rdb * kSlabFloats * (int64_t)sizeof(float) : 0;
+}
+
 extern "C" int b200_wgrad_rdb(const void* maps_dev, const b200_wgrad_rdb_entry* entries_dev, int32_t n_rdb,
-                              int32_t n, int32_t h, int32_t w, int32_t nf, int32_t gc,
-                              b200_stream_t stream) {
+                              int32_t n, int32_t h, int32_t w, int32_t nf, int32_t gc, void* workspace,
+                              int64_t ws_bytes, b200_stream_t stream) {
   B200_REQUIRE(maps_dev && entries_dev && n_rdb > 0, "b200_wgrad_rdb: null argument");
   B200_REQUIRE(nf == 64 && gc == 32, "b200_wgrad_rdb: the fused RDB weight-gradient kernel is specialised for nf=64, gc=32");
-  static bool attr_set = false;
   const int kSmemBytes = kStages * kStageBytes + 1024;
-  if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(wgrad_rdb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
-  }
+  B200_ENSURE_SMEM(wgrad_rdb_kernel, kSmemBytes);
   RdbItemParams p;
   p.maps = reinterpret_cast<const CUtensorMap*>(maps_dev);
   p.rdbs = entries_dev;
@@ -306,29 +368,27 @@ extern "C" int b200_wgrad_rdb(const void* maps_dev, const b200_wgrad_rdb_entry* 
   p.P = (int)P;
   p.Wp = w + 2;
   p.k_steps = (int)((P + 127) / 128);
-  // Split-K for L2 locality, not for parallelism: with one item per (rdb, kernel row, type) the 148 CTAs
-  // would stream 16 different RDBs (53 MB of X/dY each) at once and every operand byte would come from
-  // HBM (18.6 GB per launch at config 2).  With S slices the CTAs in flight cover 16/S RDBs; the price is
-  // an exposed epilogue of scattered fp32 atomics per slice (single TMEM accumulator).  Measured on B200,
-  // config 2: S=1 3.76 ms, S=4 3.41 ms, S=8 4.32 ms, S=16 6.08 ms (operand phase alone: 2.55 ms for S>=4).
-  // A tap-major fp32 scratch with warp-coalesced atomics + a finalize pass was tried and is SLOWER
-  // (S=8: 5.43 ms, S=16: 8.55 ms): 32 atomics of one line serialise in one L2 slice.
-  static int ksplit_env = -1;
-  if (ksplit_env < 0) {
-    const char* e = getenv("B200_WGRAD_RDB_KSPLIT");
-    ksplit_env = e ? atoi(e) : 4;
-    if (ksplit_env < 1) ksplit_env = 1;
-  }
-  p.k_split = ksplit_env < p.k_steps ? ksplit_env : 1;
-  p.k_per = (p.k_steps + p.k_split - 1) / p.k_split;
-  p.k_split = (p.k_steps + p.k_per - 1) / p.k_per;   // no empty slices
+  rdb_split(p.k_steps, &p.k_split, &p.k_per);
   p.total_items = n_rdb * 9 * p.k_split;
   p.nf = nf;
   p.gc = gc;
+  p.ws = nullptr;
+  if (p.k_split > 1) {
+    const int64_t need = b200_wgrad_rdb_ws_bytes(n_rdb, n, h, w);
+    B200_REQUIRE(workspace && ws_bytes >= need, "b200_wgrad_rdb: workspace of %lld bytes needed (b200_wgrad_rdb_ws_bytes)",
+                 (long long)need);
+    p.ws = reinterpret_cast<float*>(workspace);
+  }
   const int sms = sm_count();
   const int grid = p.total_items < sms ? p.total_items : sms;
   ::b200::launch_kernel(wgrad_rdb_kernel, grid, kThreads, kSmemBytes, as_stream(stream), p);
   B200_LAUNCH_CHECK();
+  if (p.ws) {
+    dim3 rg(16, n_rdb);
+    ::b200::launch_kernel(wgrad_rdb_reduce_kernel, rg, 256, 0, as_stream(stream), (const float*)p.ws, entries_dev, n_rdb,
+                          p.k_split, nf, gc);
+    B200_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -7,10 +7,12 @@ Only Z is kept for backward (the activation and its LeakyReLU mask are recompute
 batch statistics).  Every train-mode forward updates running_mean / running_var /
 num_batches_tracked exactly like nn.BatchNorm2d (4 updates per training iteration).
 """
+import weakref
+
 import torch
 
 from ._lib import lib
-from .runtime import (ConvLayer, ContextPool, FlatGrads, Lease, LRELU_SLOPE, P, Plan, WeightPacker,
+from .runtime import (ConvLayer, ContextPool, pool_for, FlatGrads, Lease, LRELU_SLOPE, P, Plan, WeightPacker,
                       add_igemm, add_wgrad, make_conv_desc, require_device, taps_conv, taps_dgrad_s1,
                       taps_dgrad_s2_k4)
 
@@ -169,14 +171,17 @@ class DiscriminatorEngine:
         if S != S2:
             raise RuntimeError("Discriminator_VGG expects square inputs, got %dx%d" % (S, S2))
         key = (N, S)
-        if key not in self.pools:
-            self.pools[key] = ContextPool(lambda: self._make_context(N, S))
-        pool = self.pools[key]
+        pool = pool_for(self.pools, key, lambda: self._make_context(N, S))
         self.packer.ensure()
+        # Cache key: address + version counter + shape identify the VALUES only while the tensor that was
+        # cached is still alive (the caching allocator hands a freed address to new tensors with version 0),
+        # so the entry also holds a weak reference to that tensor: a dead reference is a miss.  A detach()ed
+        # alias (D-step: netD(fake.detach())) shares storage and version counter with the live original.
         ckey = (x.data_ptr(), x._version, tuple(x.shape))
         if self.reuse and training:
             hit = self._cache.get(ckey)
-            if hit is not None and hit[1] == self.packer.pack_count and hit[0] in pool.free:
+            if hit is not None and hit[1] == self.packer.pack_count and hit[0] in pool.free \
+                    and hit[2]() is not None:
                 ctx = hit[0]
                 pool.free.remove(ctx)
                 ctx.refinalize.run()
@@ -191,7 +196,7 @@ class DiscriminatorEngine:
         for k in [k for k, v in self._cache.items() if v[0] is ctx]:
             del self._cache[k]
         if self.reuse and training:
-            self._cache[ckey] = (ctx, self.packer.pack_count)
+            self._cache[ckey] = (ctx, self.packer.pack_count, weakref.ref(x))
         ctx.x.copy_(x)
         ctx.trained = bool(training)
         if training:

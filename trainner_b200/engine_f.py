@@ -8,8 +8,9 @@ of the layer below, MaxPool backward routes to the first maximum (torch semantic
 """
 import torch
 
+from . import _lib
 from ._lib import lib
-from .runtime import (ConvLayer, ContextPool, Lease, P, Plan, WeightPacker, add_igemm, make_conv_desc,
+from .runtime import (ConvLayer, ContextPool, pool_for, Lease, P, Plan, WeightPacker, add_igemm, make_conv_desc,
                       require_device, taps_conv, taps_dgrad_s1)
 
 BF16 = torch.bfloat16
@@ -138,15 +139,14 @@ class FeatureEngine:
         self._ensure(x)
         N, _, H, W = x.shape
         key = (N, H, W)
-        if key not in self.pools:
-            self.pools[key] = ContextPool(lambda: self._make_context(N, H, W))
-        pool = self.pools[key]
-        ctx = pool.acquire()
-        self.packer.ensure()
-        for k in listen:
-            if k in self.unavailable or k not in ctx.taps:
+        pool = pool_for(self.pools, key, lambda: self._make_context(N, H, W))
+        names = [o[3] for o in self.ops]
+        for k in listen:   # validate BEFORE leasing a context (a raise must not leak it)
+            if k in self.unavailable or k not in names:
                 raise NotImplementedError("B200 FeatureExtractor: tap '%s' is not materialised (pre-ReLU taps "
                                           "exist only for the last extracted layer)" % k)
+        ctx = pool.acquire()
+        self.packer.ensure()
         ctx.x.copy_(x)
         ctx.fwd.run()
         outs = {k: ctx.taps[k].clone() for k in listen}
@@ -170,6 +170,13 @@ class FeatureEngine:
                 raise NotImplementedError("B200 FeatureExtractor backward: gradient taps other than the last "
                                           "layer of the extracted stack are not implemented")
             ctx.dT[last].copy_(gten)
+            if self.ops[last][2]:
+                # the tap is a ReLU OUTPUT ('reluX_Y'): the incoming gradient is wrt the activation, the dgrad
+                # chain starts from the pre-activation gradient -> apply this layer's own ReLU mask first
+                t = ctx.T[last]
+                _lib.check(lib.b200_lrelu_mask_mul(ctx.dT[last].data_ptr(), t.data_ptr(), ctx.dT[last].data_ptr(),
+                                                   t.numel(), 0.0, torch.cuda.current_stream().cuda_stream),
+                           "lrelu_mask_mul")
         ctx.bwd.run()
         dx = ctx.dx.clone()
         lease.release()

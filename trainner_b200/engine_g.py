@@ -19,9 +19,9 @@ import os
 import torch
 
 from . import _lib
-from ._lib import ColsumEntry, PackCatEntry, RdbDesc, WgradRdbEntry, lib
+from ._lib import ChainDesc, ChainStage, ColsumEntry, PackCatEntry, RdbDesc, WgradRdbEntry, lib
 from .runtime import sm_count_hint
-from .runtime import (ConvLayer, ContextPool, FlatGrads, Lease, LRELU_SLOPE, P, Plan, WeightPacker,
+from .runtime import (ConvLayer, ContextPool, pool_for, FlatGrads, Lease, LRELU_SLOPE, P, Plan, WeightPacker,
                       add_flat, add_igemm, add_wgrad, make_conv_desc, make_flat_desc, require_device, taps_conv,
                       taps_dgrad_s1)
 
@@ -86,16 +86,24 @@ class RRDBNetEngine:
         # (~10k cycles/stage vs ~3.5k cycles of MMA; profiles/r01_rdb_persist_timeline.txt) makes it no
         # faster than the flat per-conv kernels at 16 images/GPU, so the flat path stays the default.
         self.persist = os.environ.get("B200_RDB_PERSIST", "0") == "1"
+        # Whole-trunk chain (csrc/rdb_chain.cu): the same stage-merged form with the slices kept in shared memory
+        # and ONE launch per image group for all dense blocks -- the default trunk path (B200_TRUNK_CHAIN=0: the
+        # per-conv flat kernels).  Shapes it does not cover (w > 128, nf != 64, gc != 32) use the flat kernels.
+        self.chain = os.environ.get("B200_TRUNK_CHAIN", "1") == "1" and nf == 64 and gc == 32 and not self.persist
         self.wstage_f, self.wstage_b = [], []
-        if self.persist:
+        nrdb_ = len(self.rdbs)
+        if self.persist or self.chain:
+            # stage weights of all blocks, contiguous per stage: WF[j][r], WB[j][nrdb-1-r] (chain order of the backward)
+            self.WF = [torch.zeros(nrdb_, 9, 192 - 32 * j, nf if j == 0 else gc, dtype=BF16, device=device) for j in range(5)]
+            self.WB = [torch.zeros(nrdb_, 9, 192 - 32 * j, nf if j == 0 else gc, dtype=BF16, device=device) for j in range(5)]
             for r, convs in enumerate(self.rdbs):
                 a = 0.04 if r % 3 == 2 else 0.2
                 wf, wb = [], []
                 for j in range(5):
                     n_j = 192 - 32 * j
                     kc = nf if j == 0 else gc   # stage input channels = packed K width (64 or 32)
-                    tf = torch.zeros(9, n_j, kc, dtype=BF16, device=device)
-                    tb = torch.zeros(9, n_j, kc, dtype=BF16, device=device)
+                    tf = self.WF[j][r]
+                    tb = self.WB[j][nrdb_ - 1 - r]
                     ci_off, n_ci = (0, nf) if j == 0 else (nf + (j - 1) * gc, gc)
                     for kk in range(j, 5):
                         cv = convs[kk]
@@ -127,6 +135,20 @@ class RRDBNetEngine:
             g -= 1
         if g < 1:
             raise RuntimeError("RRDBNet: image too large for the persistent dense-block kernel")
+        return [(i, min(g, N - i)) for i in range(0, N, g)]
+
+    @staticmethod
+    def _chain_geometry(n, h, w):
+        n_cta, ll = CT.c_int32(0), CT.c_int64(0)
+        lib.b200_rdb_chain_geometry(n, h, w, CT.byref(n_cta), CT.byref(ll))
+        return n_cta.value, ll.value
+
+    def _chain_groups(self, N, h, w):
+        """image groups of one rdb_chain launch: two position ranges (halves of the group) of <= #SM 128-row tiles"""
+        half = (sm_count_hint() * 128) // ((h + 2) * (w + 2))
+        if half < 1:
+            return None
+        g = 2 * half
         return [(i, min(g, N - i)) for i in range(0, N, g)]
 
     # ------------------------------------------------------------------ plans
@@ -168,9 +190,42 @@ class RRDBNetEngine:
         f.add(lib.b200_conv3x3_thin_to_wide, P(ctx.x), P(self.fea.weight), P(self.fea.bias), P(ctx.F0),
               N, h, w, net.in_nc, nf, nf, 0, 0, None, None, 0, 0.0, None, 0, 0, 0.0)
         f.add(lib.b200_pad_copy, P(ctx.B[0]), Bc[0], 0, P(ctx.F0), nf, 0, N, h, w, nf)
-        groups = self._image_groups(N, h, w)
-        ctx.flags = torch.zeros(256, dtype=torch.int32, device=dev)
-        for r, convs in enumerate(self.rdbs):
+        groups = self._image_groups(N, h, w) if self.persist else []
+        ctx.flags = torch.zeros(256, dtype=torch.int32, device=dev) if self.persist else None
+        use_chain = self.chain and w + 3 <= 131
+        ctx.chain_groups = self._chain_groups(N, h, w) if use_chain else None
+        use_chain = ctx.chain_groups is not None
+        if use_chain:
+            ll_bytes = max(self._chain_geometry(gn, h, w)[1] for _, gn in ctx.chain_groups)
+            ctx.ll = torch.zeros(ll_bytes, dtype=torch.uint8, device=dev)
+            ctx.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+            entries = []
+            for r, convs in enumerate(self.rdbs):
+                Bi, Bo = ctx.B[r], ctx.B[r + 1]
+                last_of_rrdb = (r % 3 == 2)
+                for j in range(5):
+                    e = ChainStage()
+                    e.bias = convs[j].bias.data_ptr()
+                    e.alpha, e.slope = 1.0, LRELU_SLOPE
+                    if j < 4:
+                        e.out, e.out_c, e.out_coff, e.act = Bi.data_ptr(), C, nf + j * gc, 1
+                    else:
+                        e.out, e.out_c, e.out_coff, e.act = Bo.data_ptr(), Bc[r + 1], 0, 0
+                        e.alpha = 0.04 if last_of_rrdb else 0.2
+                        e.res1, e.res1_c, e.res1_coff, e.beta1 = Bi.data_ptr(), C, 0, (0.2 if last_of_rrdb else 1.0)
+                        if last_of_rrdb:
+                            e.res2, e.res2_c, e.res2_coff, e.beta2 = ctx.B[r - 2].data_ptr(), C, 0, 1.0
+                    entries.append(e)
+            ctx.chain_tab_f = torch.frombuffer(bytearray(bytes((ChainStage * len(entries))(*entries))),
+                                               dtype=torch.uint8).to(dev)
+            ctx.chain_wf = (CT.c_void_p * 5)(*[t.data_ptr() for t in self.WF])
+            rdb_flops = 2.0 * h * w * 9 * (nf * gc + (nf + gc) * gc + (nf + 2 * gc) * gc + (nf + 3 * gc) * gc + C * nf)
+            for (g0, gn) in ctx.chain_groups:
+                d = ChainDesc(N, g0, gn, h, w, C, 0, nrdb, 0)
+                f.keep(d)
+                f.add(lib.b200_rdb_chain, CT.byref(d), P(ctx.B[0]), ctx.chain_wf, P(ctx.chain_tab_f), P(ctx.ll), ll_bytes,
+                      P(ctx.epoch), flops=rdb_flops * gn * nrdb, tag="rdb_chain", info="fwd %d img x %d blocks" % (gn, nrdb))
+        for r, convs in enumerate([] if use_chain else self.rdbs):
             Bi, Bo = ctx.B[r], ctx.B[r + 1]
             last_of_rrdb = (r % 3 == 2)
             a = 0.04 if last_of_rrdb else 0.2
@@ -321,7 +376,36 @@ class RRDBNetEngine:
         add_igemm(b, d, dT, L.w_dgr, y=slot(nrdb))
         # x flat (its own border is the conv's zero padding -> pad 0 on the flat grid), dy dense
         add_wgrad(b, N, Hp, Wp, nf, 0, nf, h, w, nf, 0, nf, 3, 1, 0, 1.0, ctx.B[nrdb], dT, g(L.weight), g(L.bias))
-        for r in range(nrdb - 1, -1, -1):
+        use_chain = ctx.chain_groups is not None
+        if use_chain:
+            entries = []
+            for r in range(nrdb - 1, -1, -1):
+                Gr, dO, Br = slot(r), slot(r + 1), ctx.B[r]
+                last_of_rrdb, first_of_rrdb = (r % 3 == 2), (r % 3 == 0)
+                for j in range(5):
+                    e = ChainStage()
+                    e.alpha, e.mask_slope = 1.0, SL
+                    e.out, e.out_c = Gr.data_ptr(), CC
+                    if j < 4:
+                        e.out_coff = nf + (3 - j) * gc
+                        e.mask, e.mask_c, e.mask_coff = Br.data_ptr(), CC, nf + (3 - j) * gc
+                    else:
+                        e.out_coff = 0
+                        e.res1, e.res1_c, e.res1_coff, e.beta1 = dO.data_ptr(), CC, 0, (0.2 if last_of_rrdb else 1.0)
+                        if first_of_rrdb:
+                            e.res2, e.res2_c, e.res2_coff, e.beta2 = slot(r + 3).data_ptr(), CC, 0, 1.0
+                    entries.append(e)
+            ctx.chain_tab_b = torch.frombuffer(bytearray(bytes((ChainStage * len(entries))(*entries))),
+                                               dtype=torch.uint8).to(dev)
+            ctx.chain_wb = (CT.c_void_p * 5)(*[t.data_ptr() for t in self.WB])
+            rdb_flops = 2.0 * h * w * 9 * (nf * gc + (nf + gc) * gc + (nf + 2 * gc) * gc + (nf + 3 * gc) * gc + CC * nf)
+            for (g0, gn) in ctx.chain_groups:
+                d = ChainDesc(N, g0, gn, h, w, CC, 0, nrdb, 1)
+                b.keep(d)
+                b.add(lib.b200_rdb_chain, CT.byref(d), P(slot(nrdb)), ctx.chain_wb, P(ctx.chain_tab_b), P(ctx.ll),
+                      ctx.ll.numel(), P(ctx.epoch), flops=rdb_flops * gn * nrdb, tag="rdb_chain",
+                      info="bwd %d img x %d blocks" % (gn, nrdb))
+        for r in range(nrdb - 1, -1, -1) if not use_chain else []:
             convs = self.rdbs[r]
             Gr, dO, Br = slot(r), slot(r + 1), ctx.B[r]
             last_of_rrdb = (r % 3 == 2)
@@ -395,7 +479,9 @@ class RRDBNetEngine:
         to_dev = lambda arr: torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
         ctx.wg_entries = to_dev((WgradRdbEntry * len(entries))(*entries))
         ctx.wg_sums = to_dev((ColsumEntry * len(sums))(*sums))
-        b.add(lib.b200_wgrad_rdb, P(ctx.wg_maps), P(ctx.wg_entries), nrdb, N, h, w, nf, gc,
+        ws_bytes = int(lib.b200_wgrad_rdb_ws_bytes(nrdb, N, h, w))
+        ctx.wg_ws = torch.empty(max(ws_bytes, 4) // 4, dtype=torch.float32, device=dev)
+        b.add(lib.b200_wgrad_rdb, P(ctx.wg_maps), P(ctx.wg_entries), nrdb, N, h, w, nf, gc, P(ctx.wg_ws), ws_bytes,
               flops=2.0 * N * h * w * 9 * nrdb * (nf * gc + (nf + gc) * gc + (nf + 2 * gc) * gc + (nf + 3 * gc) * gc + CC * nf),
               tag="wgrad_rdb", info="%d RDBs" % nrdb)
         b.add(lib.b200_colsum_multi, P(ctx.wg_sums), len(sums))
@@ -411,9 +497,7 @@ class RRDBNetEngine:
         self._ensure(x)
         N, _, h, w = x.shape
         key = (N, h, w)
-        if key not in self.pools:
-            self.pools[key] = ContextPool(lambda: self._make_context(N, h, w))
-        pool = self.pools[key]
+        pool = pool_for(self.pools, key, lambda: self._make_context(N, h, w))
         ctx = pool.acquire()
         self.packer.ensure()
         ctx.x.copy_(x)

@@ -49,7 +49,8 @@ class SRModel:
         netF = None
         if train_opt.get("feature_weight"):
             popt = train_opt.get("perceptual_opt") or {}
-            netF = networks.define_F(load_path=popt.get("pretrained_path")).to(self.device)
+            z_norm = bool(((opt.get("datasets") or {}).get("train") or {}).get("znorm", False))   # networks.py:322
+            netF = networks.define_F(load_path=popt.get("pretrained_path"), z_norm=z_norm).to(self.device)
         self.generatorlosses = losses.GeneratorLoss(train_opt.get("pixel_weight", 0),
                                                    train_opt.get("feature_weight", 0), netF)
         if self.cri_gan:
@@ -67,7 +68,18 @@ class SRModel:
                 betas=(train_opt.get("beta1_D", 0.9), train_opt.get("beta2_D", 0.999)),
                 weight_decay=train_opt.get("weight_decay_D", 0) or 0)
             self.optimizers.append(self.optimizer_D)
-        self.accumulations = 1
+        # virtual batch (base_model.py:722-734): gradients accumulate over `accumulations` iterations
+        ds = (opt.get("datasets") or {}).get("train") or {}
+        bs, vb = ds.get("batch_size"), ds.get("virtual_batch_size")
+        self.accumulations = (vb // bs) if (bs and vb and vb > bs) else 1
+        # gradient clipping of G before its optimizer step (base_model.py:774-787, 911-922)
+        self.grad_clip = None
+        gc = train_opt.get("grad_clip")
+        if gc:
+            self.grad_clip = torch.nn.utils.clip_grad_value_ if str(gc).lower() == "value" \
+                else torch.nn.utils.clip_grad_norm_
+            self.grad_clip_value = train_opt.get("grad_clip_value", 0.1)
+            self.grad_history = []
         self.outm = train_opt.get("finalcap", None)
         self.log_dict = LazyLog()
         self.exchange = GradExchange()
@@ -125,6 +137,8 @@ class SRModel:
         if step % self.accumulations == 0:
             net = self.netG if opt_flag == "G" else self.netD
             self.exchange.all_reduce_grads(net)
+            if opt_flag == "G":
+                self.apply_gradclip()
             optimizer.step()
             optimizer.zero_grad()
             self._mark_dirty(net)
@@ -132,6 +146,18 @@ class SRModel:
                 self.optGstep = True
             else:
                 self.optDstep = True
+
+    def apply_gradclip(self):
+        """base_model.py:911-922 (+ get_auto_norm :897-909): clip G's gradients by value or by norm; 'auto' clips
+        to the 10th percentile of the gradient-norm history."""
+        if self.grad_clip is None:
+            return
+        value = self.grad_clip_value
+        if value == "auto":
+            sq = torch.stack([p.grad.detach().float().norm(2) ** 2 for p in self.netG.parameters() if p.grad is not None])
+            self.grad_history.append(float(sq.sum().sqrt()))
+            value = float(torch.quantile(torch.tensor(self.grad_history, dtype=torch.float32), 0.10))
+        self.grad_clip(self.netG.parameters(), value)
 
     def optimize_parameters(self, step):
         eff_step = step / self.accumulations

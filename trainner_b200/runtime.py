@@ -275,6 +275,26 @@ class ContextPool:
     def release(self, ctx):
         self.free.append(ctx)
 
+    def in_use(self):
+        return len(self.all) - len(self.free)
+
+
+def pool_for(pools, key, factory, max_shapes=4):
+    """Per-shape workspace pools with an LRU cap: validating over images of many sizes would otherwise
+    keep one full activation (+ gradient) workspace per distinct shape forever.  Pools with a leased
+    context are never evicted."""
+    pool = pools.get(key)
+    if pool is not None:
+        pools[key] = pools.pop(key)    # most recently used last
+        return pool
+    while len(pools) >= max_shapes:
+        victim = next((k for k, p in pools.items() if p.in_use() == 0), None)
+        if victim is None:
+            break
+        del pools[victim]
+    pool = pools[key] = ContextPool(factory)
+    return pool
+
 
 class Lease:
     def __init__(self, pool, ctx):
