@@ -123,40 +123,23 @@ __device__ __forceinline__ bool det_arrive_last(unsigned* counter, unsigned nblk
   return last;
 }
 
-// Run by the last block (all blockDim.x = 256 threads): out(k, sum_b part[b * nout + k]) for k < nout, the
-// sum taken in a FIXED order -- G = 256 / nout thread groups take interleaved block subsets (b = g, g+G, ...)
-// and their partial sums are combined in group order through `sh` (256 floats of shared memory).
+// Run by the last block (all 256 threads = 8 warps): out(k, sum_b part[k * nblk + b]) for k < nout, the sum
+// taken in a FIXED order: warp w owns outputs k = w, w + 8, ..; its lanes add the blocks b = lane, lane + 32, ..
+// (coalesced, all loads independent) and the 32 lane sums are combined by a shuffle tree.  `sh` is unused
+// (kept for call-site compatibility).  Partials are laid out OUTPUT-major: part[k * nblk + b].
 template <typename F>
 __device__ __forceinline__ void det_sum_blocks(const float* __restrict__ part, unsigned nblk, int nout, float* sh,
                                                F&& out) {
-  const int tid = threadIdx.x;
-  if (nout >= 128) {
-    for (int k = tid; k < nout; k += 256) {
-      float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-      unsigned b = 0;
-      for (; b + 3 < nblk; b += 4) {
-        t0 += part[(size_t)b * nout + k];
-        t1 += part[(size_t)(b + 1) * nout + k];
-        t2 += part[(size_t)(b + 2) * nout + k];
-        t3 += part[(size_t)(b + 3) * nout + k];
-      }
-      for (; b < nblk; ++b) t0 += part[(size_t)b * nout + k];
-      out(k, (t0 + t1) + (t2 + t3));
-    }
-    return;
-  }
-  int G = 256 / nout;
-  const int g = tid / nout, k = tid - g * nout;
-  float t = 0.f;
-  if (g < G)
-    for (unsigned b = g; b < nblk; b += G) t += part[(size_t)b * nout + k];
-  __syncthreads();
-  sh[tid] = t;
-  __syncthreads();
-  if (tid < nout) {
-    float tot = 0.f;
-    for (int q = 0; q < G; ++q) tot += sh[q * nout + tid];
-    out(tid, tot);
+  (void)sh;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarp = blockDim.x >> 5;
+  for (int k = warp; k < nout; k += nwarp) {
+    const float* row = part + (size_t)k * nblk;
+    float t = 0.f;
+    for (unsigned b = lane; b < nblk; b += 32) t += row[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) out(k, t);
   }
 }
 #endif

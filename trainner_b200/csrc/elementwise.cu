@@ -116,7 +116,7 @@ __global__ void bn_reduce_kernel(const __nv_bfloat16* __restrict__ z,
     const int ln = ch >> 3, j = (ch & 7) + 8 * which;
     float t = 0.f;
     for (int q = ln; q < 256; q += vec_per_pix) t += sh[j * 256 + q];
-    part[(size_t)blockIdx.x * 2 * c + k] = t;
+    part[(size_t)k * gridDim.x + blockIdx.x] = t;
   }
   // deterministic grid reduction: the last block to arrive adds the per-block partials in block order
   if (det_arrive_last(counter, gridDim.x))

@@ -40,8 +40,8 @@ namespace {
 constexpr int kThreads = 352;          // weights producer, 2 MMA issuers, 2 x 4 epilogue warps
 constexpr int kTileM = 128;
 constexpr int kNTotal = 192;
-constexpr int kBStages = 4;
-constexpr uint32_t kBStageBytes = 32 * 1024;   // one 64-channel tap tile (24 KB) or three 32-channel tap tiles (<= 30 KB)
+constexpr int kBStages = 3;
+constexpr uint32_t kBStageBytes = 24 * 1024;   // one 64-channel tap tile (24 KB) or 2-3 32-channel tap tiles (<= 24 KB)
 constexpr int kLLRowBytes = 256;       // 128 B of data (64 channels) in LL form
 constexpr int kMaxHalo = 131;          // w <= 128
 
@@ -59,6 +59,7 @@ struct ChainParams {
   uint32_t ll_tile_stride; // bytes per (range, tile)
   const uint32_t* epoch;   // launch sequence number (bumped by a 1-thread kernel before this one)
   int skew_cycles;         // tile 1 starts this many cycles after tile 0 (de-phases the two pipelines)
+  int cluster_size;        // CTAs per thread-block cluster (1: every halo goes through L2)
   long long* dbg;
 };
 
@@ -157,28 +158,60 @@ __device__ __forceinline__ void finish32(const b200_chain_stage& e, const uint32
 
 #define CDBG(slot) do { if (p.dbg && lane == 0) p.dbg[(long long)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// bulk copy local shared memory -> a peer CTA's shared memory; completes `bytes` on the PEER's mbarrier
+__device__ __forceinline__ void dsmem_push(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ int taps_per_slot(int j) { return j == 0 ? 1 : (j == 1 ? 2 : 3); }
+
 __global__ void __launch_bounds__(kThreads, 1)
 rdb_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t b_full[kBStages], b_empty[kBStages], init_full[2], slice_ready[2], acc_ready[2];
+  // slice_ready[tile][parity]: operand region (tile, parity) complete = 4 epilogue warps (own rows, cluster-edge
+  // halos) + 1 expect_tx arrival covering the bytes the in-cluster neighbours push through DSMEM
+  __shared__ uint64_t b_full[kBStages], b_empty[kBStages], init_full[2], slice_ready[2][2], acc_ready[2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int cta = blockIdx.x;
+  const int crank = p.cluster_size > 1 ? (int)cluster_ctarank() : 0;
   // tile `t` of this CTA = tile number `cta` of position range t; inactive when the range has fewer tiles
   const bool active0 = cta < p.range_tiles[0], active1 = cta < p.range_tiles[1];
   const int n_active = (active0 ? 1 : 0) + (active1 ? 1 : 0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kBStages; ++s) {
       mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], n_active);
+      mbar_init(&b_empty[s], n_active > 0 ? n_active : 1);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&init_full[t], 1);
-      mbar_init(&slice_ready[t], 4);   // one arrival per epilogue warp of the tile
+      mbar_init(&slice_ready[t][0], 5);
+      mbar_init(&slice_ready[t][1], 5);
       mbar_init(&acc_ready[t], 1);
     }
     mbar_fence_init();
@@ -187,11 +220,21 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
     tmem_alloc(&tmem_base_s, 512);
     tmem_relinquish();
   }
+  // halo rows of the second (never TMA-loaded) operand region of each tile start as zeros: at the ends of a
+  // position range nobody ever writes them (the neighbouring positions are border rows of other images)
+  for (int i = threadIdx.x; i < 2 * 2 * p.halo * 8; i += kThreads) {
+    const int t = i / (2 * p.halo * 8), k = i % (2 * p.halo * 8);
+    const int row = k >> 3, ch = k & 7;
+    const uint32_t R = row < p.halo ? (uint32_t)row : (uint32_t)(kTileM + row);
+    *reinterpret_cast<uint4*>(smem + (size_t)(t * 2 + 1) * p.a_region_bytes + (size_t)R * 128 + ch * 16) = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (p.cluster_size > 1) cluster_sync_all();   // every CTA's barriers are initialised before any peer pushes into it
   const uint32_t tmem = tmem_base_s;
-  const uint32_t b_ring_off = 2 * p.a_region_bytes;
+  const uint32_t b_ring_off = 4 * p.a_region_bytes;
   const int n_stages_total = p.n_blocks * 5;
   if (warp == 0) CDBG(0);
 
@@ -203,7 +246,7 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
       for (int t = 0; t < 2; ++t) {
         if (!(t == 0 ? active0 : active1)) continue;
         const int row0 = p.range_pos0[t] + cta * kTileM - p.halo;
-        uint8_t* sa = smem + (size_t)t * p.a_region_bytes;
+        uint8_t* sa = smem + (size_t)(t * 2) * p.a_region_bytes;
         mbar_expect_tx(&init_full[t], p.a_bytes);
         for (int bx = 0; bx < p.nbox; ++bx)
           tma_load_2d(sa + (size_t)bx * p.box_rows * 128, &p.x_map, &init_full[t], p.x_ch, row0 + bx * p.box_rows);
@@ -216,14 +259,15 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
       for (int blk = 0; blk < p.n_blocks; ++blk) {
         for (int j = 0; j < 5; ++j) {
           const int N = kNTotal - 32 * j;
-          const int tpb = (j == 0) ? 1 : 3;   // taps per weight slot
+          const int tpb = taps_per_slot(j);
           const uint32_t tap_bytes = (uint32_t)N * (j == 0 ? 128 : 64);
           const int row_base = blk * 9 * N;
           for (int t0 = 0; t0 < 9; t0 += tpb) {
+            const int nt = (9 - t0) < tpb ? (9 - t0) : tpb;
             mbar_wait(&b_empty[bs], bph ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(&b_full[bs], tap_bytes * tpb);
-              for (int q = 0; q < tpb; ++q)
+              mbar_expect_tx(&b_full[bs], tap_bytes * nt);
+              for (int q = 0; q < nt; ++q)
                 tma_load_2d(smem + b_ring_off + (size_t)bs * kBStageBytes + (size_t)q * tap_bytes, &p.w_map[j],
                             &b_full[bs], 0, row_base + (t0 + q) * N);
             }
@@ -244,7 +288,6 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
       const uint64_t desc_hi = make_smem_desc(0, 16, 1024, LAYOUT_SW128, 0);
       const uint64_t desc_b64 = make_smem_desc(0, 16, 512, LAYOUT_SW64, 0);   // 32-channel weight tiles: 64-byte rows
       const uint32_t smem_base = smem_u32(smem);
-      const uint32_t a_base = smem_base + tile * p.a_region_bytes + (uint32_t)p.halo * 128;
       const uint32_t d_tile = tmem + tile * kNTotal;
       uint32_t sh16[9];
 #pragma unroll
@@ -255,7 +298,7 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
         }
       }
       int bs = 0;
-      uint32_t bph = 0, ready_ph = 0;
+      uint32_t bph = 0;
       for (int s = 0; s < n_stages_total; ++s) {
         const int j = s % 5;
         const int N = kNTotal - 32 * j;
@@ -264,15 +307,15 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
         if (s == 0) {
           mbar_wait(&init_full[tile], 0);
         } else {
-          mbar_wait(&slice_ready[tile], ready_ph);
-          ready_ph ^= 1;
+          mbar_wait(&slice_ready[tile][s & 1], (uint32_t)(((s - 1) >> 1) & 1));
         }
         tc_fence_after();
-        if (s < 16 && tile == 0) CDBG(2 + 3 * s);   // operand slice ready
-        const int tpb = (j == 0) ? 1 : 3;
+        if (s < 7 && tile == 0) CDBG(2 + 8 * s);   // operand slice ready
+        const int tpb = taps_per_slot(j);
         const uint32_t tap16 = ((uint32_t)N * (j == 0 ? 128 : 64)) >> 4;
-        const uint32_t a16 = a_base >> 4;
+        const uint32_t a16 = (smem_base + (uint32_t)(tile * 2 + (s & 1)) * p.a_region_bytes + (uint32_t)p.halo * 128) >> 4;
         for (int t0 = 0; t0 < 9; t0 += tpb) {
+          const int nt = (9 - t0) < tpb ? (9 - t0) : tpb;
           mbar_wait(&b_full[bs], bph);
           tc_fence_after();
           const uint32_t b16 = (smem_base + b_ring_off + bs * kBStageBytes) >> 4;
@@ -284,8 +327,7 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
                 umma_f16(d_tmem, desc_hi | (uint64_t)((at + 2 * k) & 0x3FFF), desc_hi | (uint64_t)((b16 + 2 * k) & 0x3FFF), idesc,
                          (t0 | k) != 0);
             } else {
-#pragma unroll
-              for (int q = 0; q < 3; ++q) {
+              for (int q = 0; q < nt; ++q) {
                 const uint32_t at = a16 + sh16[t0 + q], bt = b16 + q * tap16;
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
@@ -302,7 +344,7 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
             bph ^= 1;
           }
         }
-        if (s < 16 && tile == 0) CDBG(3 + 3 * s);   // stage MMAs issued
+        if (s < 7 && tile == 0) CDBG(3 + 8 * s);   // stage MMAs issued
       }
     }
   } else {
@@ -319,29 +361,41 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
       const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
       const bool valid = lpos < p.range_len[tile] && yp >= 1 && yp <= p.h && xp >= 1 && xp <= p.w;
       const bool has_up = cta > 0, has_dn = cta + 1 < p.range_tiles[tile];
+      // neighbours inside the cluster are reached through distributed shared memory, the others through L2 (LL)
+      const bool ds_up = has_up && crank > 0, ds_dn = has_dn && crank + 1 < p.cluster_size;
+      const bool ll_up = has_up && !ds_up, ll_dn = has_dn && !ds_dn;
       const uint32_t t_row = tmem + ((uint32_t)(quad * 32) << 16) + tile * kNTotal;
-      const uint32_t region = smem_u32(smem) + tile * p.a_region_bytes;
+      const uint32_t region0 = smem_u32(smem) + (uint32_t)(tile * 2) * p.a_region_bytes;
       const uint32_t own_row = (uint32_t)(p.halo + r);
-      const uint32_t own_addr = region + own_row * 128;
       const uint32_t own_xor = own_row & 7;
-      uint8_t* ll_me = p.ll + ((size_t)tile * gridDim.x + cta) * p.ll_tile_stride;
-      uint8_t* ll_up = ll_me - p.ll_tile_stride;   // receive buffers of tile - 1 / tile + 1 of the same range
-      uint8_t* ll_dn = ll_me + p.ll_tile_stride;
+      uint8_t* ll_me = p.ll + ((size_t)tile * p.range_tiles[0] + cta) * p.ll_tile_stride;
+      uint8_t* ll_upb = ll_me - p.ll_tile_stride;   // receive buffers of tile - 1 / tile + 1 of the same range
+      uint8_t* ll_dnb = ll_me + p.ll_tile_stride;
       const uint32_t side_bytes = (uint32_t)p.halo * kLLRowBytes;   // one (side, parity) buffer
       const uint32_t flag0 = (*p.epoch) << 12;
+      const uint32_t push_bytes = (uint32_t)p.halo * 128;
+      const uint32_t ds_in_bytes = ((ds_up ? 1u : 0u) + (ds_dn ? 1u : 0u)) * push_bytes;
       uint32_t acc_ph = 0;
       for (int s = 0; s < n_stages_total; ++s) {
         const int j = s % 5;
         const b200_chain_stage e = p.table[s];
         const int nch = (j == 4) ? 8 : 4;              // 16-byte chunks of the finished slice (64 or 32 channels)
         const uint32_t flag = flag0 + (uint32_t)s + 1u;
-        const int par = s & 1;
+        const int par = s & 1, pn = par ^ 1;           // the finished slice becomes operand region `pn`
+        const bool more = s + 1 < n_stages_total;
+        const uint32_t region = region0 + (uint32_t)pn * p.a_region_bytes;
+        const uint32_t own_addr = region + own_row * 128;
+        if (more && et == 0) {
+          // this phase of slice_ready[tile][pn] also waits for the bytes the in-cluster neighbours push
+          if (ds_in_bytes) mbar_expect_tx(&slice_ready[tile][pn], ds_in_bytes);
+          else mbar_arrive(&slice_ready[tile][pn]);
+        }
         EpiPre q;
         if (valid) prefetch32(e, q, 0, m);
         mbar_wait(&acc_ready[tile], acc_ph);
         acc_ph ^= 1;
         tc_fence_after();
-        if (s < 16 && warp == 3) CDBG(4 + 3 * s);   // stage MMAs complete
+        if (s < 7 && warp == 3) CDBG(4 + 8 * s);   // stage MMAs complete
         __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(e.out);
         for (int c0 = 0; c0 < nch * 8; c0 += 32) {
           uint32_t acc[32];
@@ -356,20 +410,22 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
             for (int g = 0; g < 4; ++g) o[g] = make_uint4(0, 0, 0, 0);   // border / out-of-range positions stay zero
           }
           const int cb = c0 >> 3;   // first chunk index
-          // (1) own rows of the next operand slice, 128B-swizzled K-major
+          // (1) own rows of the next operand slice, 128B-swizzled K-major (the in-cluster halo pushes read them)
+          if (more) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) st_shared_v4(own_addr + ((uint32_t)((cb + g) ^ own_xor) << 4), o[g]);
-          // (2) halo rows for the neighbouring tiles (LL: data + flag in every 8 bytes)
-          if (has_up && r < p.halo) {
-            uint8_t* dst = ll_up + (1 * 2 + par) * side_bytes + (size_t)r * kLLRowBytes + cb * 32;
+            for (int g = 0; g < 4; ++g) st_shared_v4(own_addr + ((uint32_t)((cb + g) ^ own_xor) << 4), o[g]);
+          }
+          // (2) halo rows for neighbours in OTHER clusters through L2 (LL: data + flag in every 8 bytes)
+          if (more && ll_up && r < p.halo) {
+            uint8_t* dst = ll_upb + (1 * 2 + par) * side_bytes + (size_t)r * kLLRowBytes + cb * 32;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               st_global_v4(dst + g * 32, o[g].x, flag, o[g].y, flag);
               st_global_v4(dst + g * 32 + 16, o[g].z, flag, o[g].w, flag);
             }
           }
-          if (has_dn && r >= kTileM - p.halo) {
-            uint8_t* dst = ll_dn + (0 * 2 + par) * side_bytes + (size_t)(r - (kTileM - p.halo)) * kLLRowBytes + cb * 32;
+          if (more && ll_dn && r >= kTileM - p.halo) {
+            uint8_t* dst = ll_dnb + (0 * 2 + par) * side_bytes + (size_t)(r - (kTileM - p.halo)) * kLLRowBytes + cb * 32;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               st_global_v4(dst + g * 32, o[g].x, flag, o[g].y, flag);
@@ -384,33 +440,82 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
           }
         }
         tc_fence_before();
-        // (4) halo rows of the finished slice from the neighbouring tiles -> own operand region
-        if (s + 1 < n_stages_total) {
-          const int per_side = p.halo * nch;
-          for (int i = et; i < 2 * per_side; i += 128) {
-            const int side = i >= per_side ? 1 : 0;
-            if (side == 0 ? !has_up : !has_dn) continue;
-            const int k = i - side * per_side;
-            const int row = k / nch, ch = k - row * nch;
-            const uint8_t* src = ll_me + (side * 2 + par) * side_bytes + (size_t)row * kLLRowBytes + ch * 32;
-            uint4 a, b;
-            do {
-              a = ld_volatile_v4(src);
-              b = ld_volatile_v4(src + 16);
-            } while (a.y != flag || a.w != flag || b.y != flag || b.w != flag);
-            const uint32_t R = side == 0 ? (uint32_t)row : (uint32_t)(p.halo + kTileM + row);
-            st_shared_v4(region + R * 128 + ((uint32_t)(ch ^ (R & 7)) << 4), make_uint4(a.x, a.z, b.x, b.z));
+        if (s < 7 && warp == 3) CDBG(6 + 8 * s);   // epilogue math + stores issued
+        if (more) {
+          fence_proxy_async();   // own rows (generic proxy) -> visible to the bulk-copy engine and the tensor core
+          // (4) push the halo rows to the in-cluster neighbours: ONE bulk copy per side, straight from this CTA's
+          //     operand region into the peer's (same 128B-swizzle phase: the row offset between the two is 128),
+          //     completing on the peer's slice_ready barrier
+          if (ds_up || ds_dn) {
+            named_bar_sync(1 + tile, 128);
+            if (et == 0) {
+              if (ds_up) {   // my rows [0, halo) -> bottom halo of the tile above
+                const uint32_t dst = mapa_cluster(region + (uint32_t)(p.halo + kTileM) * 128, (uint32_t)(crank - 1));
+                const uint32_t bar = mapa_cluster(smem_u32(&slice_ready[tile][pn]), (uint32_t)(crank - 1));
+                dsmem_push(dst, region + (uint32_t)p.halo * 128, push_bytes, bar);
+              }
+              if (ds_dn) {   // my rows [128 - halo, 128) -> top halo of the tile below
+                const uint32_t dst = mapa_cluster(region, (uint32_t)(crank + 1));
+                const uint32_t bar = mapa_cluster(smem_u32(&slice_ready[tile][pn]), (uint32_t)(crank + 1));
+                dsmem_push(dst, region + (uint32_t)kTileM * 128, push_bytes, bar);
+              }
+            }
           }
-          fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          // (5) halo rows from neighbours in other clusters: poll the LL buffers (all of a thread's polls in flight
+          //     together; items whose flags have not landed are polled again after a short sleep)
+          if (ll_up || ll_dn) {
+            const int per_side = p.halo * nch;
+            constexpr int kBatch = 5;
+            for (int base = et; base < 2 * per_side; base += 128 * kBatch) {
+              const uint8_t* src[kBatch];
+              uint32_t dst[kBatch];
+              unsigned pending = 0;
+#pragma unroll
+              for (int qi = 0; qi < kBatch; ++qi) {
+                const int i = base + qi * 128;
+                src[qi] = nullptr;
+                dst[qi] = 0;
+                if (i < 2 * per_side) {
+                  const int side = i >= per_side ? 1 : 0;
+                  if (side == 0 ? ll_up : ll_dn) {
+                    const int k = i - side * per_side;
+                    const int row = k / nch, ch = k - row * nch;
+                    src[qi] = ll_me + (side * 2 + par) * side_bytes + (size_t)row * kLLRowBytes + ch * 32;
+                    const uint32_t R = side == 0 ? (uint32_t)row : (uint32_t)(p.halo + kTileM + row);
+                    dst[qi] = region + R * 128 + ((uint32_t)(ch ^ (R & 7)) << 4);
+                    pending |= 1u << qi;
+                  }
+                }
+              }
+              while (pending) {
+                uint4 a[kBatch], b[kBatch];
+#pragma unroll
+                for (int qi = 0; qi < kBatch; ++qi)
+                  if (pending & (1u << qi)) {
+                    a[qi] = ld_volatile_v4(src[qi]);
+                    b[qi] = ld_volatile_v4(src[qi] + 16);
+                  }
+#pragma unroll
+                for (int qi = 0; qi < kBatch; ++qi)
+                  if ((pending & (1u << qi)) && a[qi].y == flag && a[qi].w == flag && b[qi].y == flag && b[qi].w == flag) {
+                    st_shared_v4(dst[qi], make_uint4(a[qi].x, a[qi].z, b[qi].x, b[qi].z));
+                    pending &= ~(1u << qi);
+                  }
+                if (pending) __nanosleep(64);
+              }
+            }
+            fence_proxy_async();
+          }
           __syncwarp();
-          if (lane == 0) mbar_arrive(&slice_ready[tile]);
+          if (lane == 0) mbar_arrive(&slice_ready[tile][pn]);
         }
-        if (s < 16 && warp == 3) CDBG(5 + 3 * s);   // slice turned around
+        if (s < 7 && warp == 3) CDBG(5 + 8 * s);   // slice turned around (this warp's part)
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cluster_size > 1) cluster_sync_all();   // no CTA of the cluster exits while a peer may still push into it
   if (warp == 0) CDBG(1);
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
@@ -458,7 +563,7 @@ extern "C" int b200_rdb_chain(const b200_chain_desc* d, const void* x0, const vo
   p.box_rows = (((region + p.nbox - 1) / p.nbox) + 7) & ~7;
   p.a_bytes = (uint32_t)p.nbox * p.box_rows * 128;
   p.a_region_bytes = (p.a_bytes + 1023) & ~1023u;
-  const int kSmemBytes = (int)(2 * p.a_region_bytes + kBStages * kBStageBytes + 1024);
+  const int kSmemBytes = (int)(4 * p.a_region_bytes + kBStages * kBStageBytes + 1024);
   B200_REQUIRE(kSmemBytes <= 227 * 1024, "b200_rdb_chain: image too wide for the shared-memory operand regions (w=%d)", d->w);
   B200_ENSURE_SMEM(rdb_chain_kernel, kSmemBytes);
   const int n0 = (d->n + 1) / 2, n1 = d->n - n0;
@@ -511,18 +616,63 @@ extern "C" int b200_rdb_chain(const b200_chain_desc* d, const void* x0, const vo
                         kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))
       return 1;
   }
+  // Thread-block clusters: neighbouring tiles inside a cluster exchange their halo rows through distributed
+  // shared memory (bulk copy + remote mbarrier), only the cluster-edge halos go through L2.  The largest cluster
+  // size (<= B200_CHAIN_CLUSTER, default 4) whose clusters are all co-resident is used.
+  static int cs_max = -1;
+  if (cs_max < 0) {
+    const char* e = getenv("B200_CHAIN_CLUSTER");
+    cs_max = e ? atoi(e) : 4;
+    if (cs_max < 1) cs_max = 1;
+    if (cs_max > 8) cs_max = 8;
+  }
+  int cs = 1, grid = n_cta;
+  for (int c = cs_max; c >= 2; c >>= 1) {
+    const int g = (n_cta + c - 1) / c * c;
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3(g);
+    q.blockDim = dim3(kThreads);
+    q.dynamicSmemBytes = kSmemBytes;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = c;
+    qa[0].val.clusterDim.y = 1;
+    qa[0].val.clusterDim.z = 1;
+    q.attrs = qa;
+    q.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, rdb_chain_kernel, &q) == cudaSuccess && max_clusters * c >= g) {
+      cs = c;
+      grid = g;
+      break;
+    }
+    (void)cudaGetLastError();
+  }
+  p.cluster_size = cs;
   ::b200::launch_kernel(chain_epoch_bump_kernel, 1, 1, 0, as_stream(stream), epoch_dev);
   B200_LAUNCH_CHECK();
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(n_cta);
+  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = as_stream(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: the neighbour exchange cannot deadlock
-  attr[0].val.cooperative = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cs > 1) {
+    // all clusters co-resident (checked above with cudaOccupancyMaxActiveClusters): the neighbour exchange
+    // cannot deadlock once every cluster is scheduled
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cs;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  } else {
+    attr[na].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident
+    attr[na].val.cooperative = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = na;
   B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rdb_chain_kernel, p));
   g_launches.fetch_add(1);
   return 0;

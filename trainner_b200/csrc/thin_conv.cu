@@ -244,13 +244,15 @@ thin_wgrad_kernel(const float* __restrict__ thin, const __nv_bfloat16* __restric
   // reduce the 4 pixel subsets into this block's partial row [64 lanes][CS*9 + 1]; the last block of the
   // channel group (blockIdx.y) to arrive adds the rows of all blocks in block order (deterministic)
   constexpr int NC1 = CS * 9 + 1;
-  float* mine = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 * NC1;
+  float* mine = part + (size_t)blockIdx.y * gridDim.x * 64 * NC1;   // output-major: [64 * NC1][gridDim.x]
 #pragma unroll
   for (int k = 0; k < NC1; ++k) {
     __syncthreads();
     red[sub][lane_c] = (k < CS * 9) ? acc[k] : bsum;
     __syncthreads();
-    if (sub == 0) mine[lane_c * NC1 + k] = red[0][lane_c] + red[1][lane_c] + red[2][lane_c] + red[3][lane_c];
+    if (sub == 0)
+      mine[(size_t)(lane_c * NC1 + k) * gridDim.x + blockIdx.x] =
+          red[0][lane_c] + red[1][lane_c] + red[2][lane_c] + red[3][lane_c];
   }
   if (det_arrive_last(counters + blockIdx.y, gridDim.x)) {
     __shared__ float shs[256];
@@ -608,8 +610,8 @@ thin_wgrad_mma_kernel(const float* __restrict__ thin, const __nv_bfloat16* __res
     __syncthreads();
   }
   // this block's partial [64][NC] -> scratch; the last block of the channel group adds all blocks in block order
-  float* mine = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 * NC;
-  for (int i = tid; i < 64 * NC; i += 256) mine[i] = red[(i / NC) * RS + (i % NC)];
+  float* mine = part + (size_t)blockIdx.y * gridDim.x * 64 * NC;   // output-major: [64 * NC][gridDim.x]
+  for (int i = tid; i < 64 * NC; i += 256) mine[(size_t)i * gridDim.x + blockIdx.x] = red[(i / NC) * RS + (i % NC)];
   if (det_arrive_last(counters + blockIdx.y, gridDim.x)) {
     __shared__ float shs[256];
     det_sum_blocks(part + (size_t)blockIdx.y * gridDim.x * 64 * NC, gridDim.x, 64 * NC, shs, [&](int i, float sv) {

@@ -136,11 +136,16 @@ class SRModel:
     def optimizer_step(self, step, optimizer, opt_flag):
         if step % self.accumulations == 0:
             net = self.netG if opt_flag == "G" else self.netD
-            self.exchange.all_reduce_grads(net)
-            if opt_flag == "G":
-                self.apply_gradclip()
-            optimizer.step()
-            optimizer.zero_grad()
+
+            def do_step():
+                if opt_flag == "G":
+                    self.apply_gradclip()
+                optimizer.step()
+                optimizer.zero_grad()
+
+            # data-parallel: gradient all-reduce + Adam run on a side stream (parallel.GradExchange.step_async);
+            # the main stream joins where the new weights are first used (optimize_parameters / backward_G)
+            self.exchange.step_async(opt_flag, net, do_step)
             self._mark_dirty(net)
             if opt_flag == "G":
                 self.optGstep = True
@@ -163,7 +168,9 @@ class SRModel:
         eff_step = step / self.accumulations
         if self.cri_gan:
             self.requires_grad(self.netD, False)
+        self.exchange.wait("G")       # G's weights of the previous iteration's update
         self.forward()
+        self.exchange.wait("D")       # D's update overlapped the G forward; its weights are needed from here on
         if (self.cri_gan is not True) or (eff_step % self.D_update_ratio == 0 and eff_step > self.D_init_iters):
             self.backward_G()
             self.optimizer_step(step, self.optimizer_G, "G")
@@ -173,6 +180,7 @@ class SRModel:
             self.optimizer_step(step, self.optimizer_D, "D")
 
     def test(self):
+        self.exchange.wait("G")
         self.netG.eval()
         with torch.no_grad():
             self.fake_H = self.netG(self.var_L)
@@ -180,6 +188,11 @@ class SRModel:
 
     def get_current_log(self):
         return self.log_dict.floats()
+
+    def synchronize(self):
+        """join the side stream (pending gradient exchange + optimizer steps); call before reading parameters"""
+        self.exchange.wait("G")
+        self.exchange.wait("D")
 
     def get_current_visuals(self, need_HR=True):
         out = OrderedDict()

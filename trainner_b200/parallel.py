@@ -43,8 +43,21 @@ def flat_buffers_of(net):
 
 
 class GradExchange:
+    """Averaging all-reduce of a network's gradients (+ its optimizer step) OFF the critical path.
+
+    The exchange of G needs nothing from the D step and vice versa: after backward_G the D step only
+    needs fake.detach() and D's weights, and after backward_D the next iteration's G forward only needs G's
+    weights.  So for world > 1 the all-reduce (ReduceOp.AVG -- no separate division pass) and the optimizer step run on
+    a side stream, ordered after the backward that produced the gradients by an event, and the main stream
+    waits for them only where the updated weights are first needed (SRModel.optimize_parameters):
+      G: exchange + Adam overlap the whole D step;   D: exchange + Adam overlap the next G forward.
+    B200_OVERLAP=0 keeps everything on the main stream."""
+
     def __init__(self, group=None):
         self.group = group
+        self._side = None
+        self._done = {}
+        self.overlap = os.environ.get("B200_OVERLAP", "1") != "0"
 
     @property
     def world(self):
@@ -58,10 +71,41 @@ class GradExchange:
                 dist.broadcast(t.data, src=src, group=self.group)
 
     def all_reduce_grads(self, net):
-        """Average gradients over ranks (sum / world, matching a mean loss over the global batch)."""
-        w = self.world
-        if w <= 1:
+        """Average gradients over ranks (matching a mean loss over the global batch), on the current stream."""
+        if self.world <= 1:
             return
+        backend = dist.get_backend(self.group)
         for buf in flat_buffers_of(net):
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
-            buf.div_(w)
+            if backend == "nccl":
+                dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group)
+            else:   # gloo (CPU tests) has no AVG
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+                buf.div_(self.world)
+
+    def step_async(self, key, net, step_fn):
+        """all-reduce `net`'s gradients and run step_fn() (clip + optimizer step + zero_grad).  world == 1, CPU or
+        B200_OVERLAP=0: inline on the current stream.  Otherwise on the side stream; wait(key) joins it."""
+        use_side = self.overlap and self.world > 1 and torch.cuda.is_available() \
+            and next(net.parameters()).is_cuda
+        if not use_side:
+            self.all_reduce_grads(net)
+            step_fn()
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ready)
+            self.all_reduce_grads(net)
+            step_fn()
+            done = torch.cuda.Event()
+            done.record(self._side)
+        self._done[key] = done
+
+    def wait(self, key):
+        """make the current stream wait for the pending exchange + optimizer step of `key` (no-op if none)"""
+        done = self._done.pop(key, None)
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
