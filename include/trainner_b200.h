@@ -279,14 +279,15 @@ int b200_bn_finalize(const float* stats, float* mean_invstd, float* running_mean
 int b200_bn_apply_lrelu(const void* z, const float* mean_invstd, const float* gamma,
                         const float* beta, void* a, int64_t npix, int32_t c, float slope,
                         b200_stream_t stream);
-/* backward: da = grad wrt lrelu output.  Pass 1 reduces sums[2][c] = (sum dzhat, sum dzhat*zhat)
- * (+ dgamma, dbeta when non-null); pass 2 writes dz.                                        */
+/* backward: da = grad wrt lrelu output.  Pass 1 reduces sums[2][c] = (sum dbn, sum dbn*zhat) deterministically and
+ * accumulates dbeta += sums[0], dgamma += sums[1] when non-null; pass 2 writes dz.  use_batch_stats = 0 is the
+ * eval()-mode backward (mean_invstd built from the running statistics: the batch-mean terms vanish).        */
 int b200_bn_bwd_reduce(const void* z, const void* da, const float* mean_invstd,
-                       const float* gamma, const float* beta, float* sums, int64_t npix, int32_t c,
-                       float slope, b200_stream_t stream);
+                       const float* gamma, const float* beta, float* sums, float* dgamma, float* dbeta,
+                       int64_t npix, int32_t c, float slope, b200_stream_t stream);
 int b200_bn_bwd_apply(const void* z, const void* da, const float* mean_invstd, const float* gamma,
-                      const float* beta, const float* sums, void* dz, float* dgamma, float* dbeta,
-                      int64_t npix, int32_t c, float slope, b200_stream_t stream);
+                      const float* beta, const float* sums, void* dz, int64_t npix, int32_t c, float slope,
+                      int32_t use_batch_stats, b200_stream_t stream);
 
 /* MaxPool2d(2,2) on NHWC bf16 (perceptual.py:158) and its backward fused with the ReLU mask
  * of the pooled activation.                                                                 */

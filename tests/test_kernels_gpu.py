@@ -267,3 +267,80 @@ def test_pixel_shuffle():
     dy = rnd(2, 16, 12, 20, seed=4)
     dz = ops.pixel_unshuffle2(nhwc(dy))
     assert torch.equal(nchw(dz), F.pixel_unshuffle(dy, 2))
+
+
+@pytest.mark.parametrize("N,H,W,nrdb", [(2, 12, 20, 2), (16, 64, 64, 3)])
+def test_wgrad_rdb_batched_kernel_direct(N, H, W, nrdb):
+    """b200_wgrad_rdb (one launch for the weight gradients of all dense blocks; position slices reduced in a fixed
+    order through the caller's workspace) called DIRECTLY through the C ABI at BASELINE config 2's tile size
+    (16 x 64 x 64), against F.conv2d autograd in fp32 on the same bf16-rounded operands, for every conv of every block.
+    Also: a second launch accumulates (+=), and two launches give bit-identical results (no float atomics)."""
+    import ctypes as CT
+    from trainner_b200 import _lib
+    from trainner_b200._lib import WgradRdbEntry, lib
+    nf, gc, C = 64, 32, 192
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(5)
+    Hp, Wp = H + 2, W + 2
+
+    def flat(ch, scale):   # zero-bordered flat NHWC bf16
+        t = torch.zeros(N, Hp, Wp, ch, dtype=BF, device=dev)
+        t[:, 1:-1, 1:-1, :] = (torch.randn(N, H, W, ch, generator=g, device=dev) * scale).to(BF)
+        return t
+
+    B = [flat(C, 1.0) for _ in range(nrdb)]
+    G = [flat(C, 0.05) for _ in range(nrdb + 1)]
+    cins = [nf + k * gc for k in range(5)]
+    couts = [gc] * 4 + [nf]
+    scale5 = [0.04 if r % 3 == 2 else 0.2 for r in range(nrdb)]
+    dw = [[torch.zeros(couts[k], cins[k], 3, 3, device=dev) for k in range(5)] for _ in range(nrdb)]
+    tmb = lib.b200_tensor_map_bytes()
+    maps_host = torch.empty(3 * nrdb * tmb + 64, dtype=torch.uint8)
+    base = (maps_host.data_ptr() + 63) // 64 * 64
+    vp = lambda xs: (CT.c_void_p * len(xs))(*xs)
+    _lib.check(lib.b200_wgrad_rdb_make_maps(base, nrdb, vp([b.data_ptr() for b in B]), vp([G[r].data_ptr() for r in range(nrdb)]),
+                                            vp([G[r + 1].data_ptr() for r in range(nrdb)]), (CT.c_int32 * nrdb)(*([C] * nrdb)),
+                                            N, H, W, C), "make_maps")
+    off = base - maps_host.data_ptr()
+    maps = maps_host[off:off + 3 * nrdb * tmb].clone().to(dev)
+    entries = []
+    for r in range(nrdb):
+        e = WgradRdbEntry()
+        for k in range(5):
+            e.dw[k] = dw[r][k].data_ptr()
+        e.scale5 = scale5[r]
+        entries.append(e)
+    ent = torch.frombuffer(bytearray(bytes((WgradRdbEntry * nrdb)(*entries))), dtype=torch.uint8).to(dev)
+    ws_bytes = int(lib.b200_wgrad_rdb_ws_bytes(nrdb, N, H, W))
+    ws = torch.empty(max(ws_bytes, 4) // 4, dtype=torch.float32, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+
+    def launch():
+        _lib.check(lib.b200_wgrad_rdb(maps.data_ptr(), ent.data_ptr(), nrdb, N, H, W, nf, gc, ws.data_ptr(), ws_bytes, s),
+                   "wgrad_rdb")
+    launch()
+    torch.cuda.synchronize()
+    first = [[t.clone() for t in row] for row in dw]
+    worst = 0.0
+    for r in range(nrdb):
+        x = B[r][:, 1:-1, 1:-1, :].float().permute(0, 3, 1, 2).contiguous()
+        for k in range(5):
+            if k < 4:
+                dy = G[r][:, 1:-1, 1:-1, nf + k * gc: nf + (k + 1) * gc]
+                sc = 1.0
+            else:
+                dy = G[r + 1][:, 1:-1, 1:-1, 0:nf]
+                sc = scale5[r]
+            dy = dy.float().permute(0, 3, 1, 2).contiguous()
+            w = torch.zeros(couts[k], cins[k], 3, 3, device=dev, requires_grad=True)
+            F.conv2d(x[:, :cins[k]], w, padding=1).backward(dy)
+            e = rel(first[r][k], sc * w.grad)
+            worst = max(worst, e)
+            assert e < 2e-3, (r, k, e)
+    print("wgrad_rdb %dx%dx%d, %d blocks: worst rel-L2 vs fp32 autograd %.2e" % (N, H, W, nrdb, worst))
+    # accumulate + determinism: a second launch adds exactly the same numbers
+    launch()
+    torch.cuda.synchronize()
+    for r in range(nrdb):
+        for k in range(5):
+            assert torch.equal(dw[r][k], first[r][k] + first[r][k]), (r, k)

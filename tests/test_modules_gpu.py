@@ -194,28 +194,56 @@ def test_training_step_vs_golden_reference(name, tmp_path):
     model.netG.load_state_dict(seeded(fx["g_shapes"], fx["g_seed"], fx["g_gain"]))
     if use_gan:
         model.netD.load_state_dict(seeded(fx["d_shapes"], fx["d_seed"]))
+    # yardstick: the reference's own bf16 path = the oracle (bit-identical op sequence, tests/test_oracle_golden.py) run
+    # under bf16 autocast on this GPU from the same weights on the same batches
+    from oracle import esrgan_oracle as O
+    o16 = None
+    if use_gan:
+        vgg_sd = O.torchvision_vgg_to_feature_net(seeded_state(tv_shapes, fx["vgg_tv_seed"])) if use_fea else None
+        o16 = O.ESRGANStepOracle(seeded(fx["g_shapes"], fx["g_seed"], fx["g_gain"]), fx["nb"],
+                                 seeded(fx["d_shapes"], fx["d_seed"]), fx["hr"], vgg_sd, pixel_weight=fx["pixel_weight"],
+                                 device="cuda")
+    problems = []
     for s, ((lr_img, hr_img), ref_log) in enumerate(zip(fx["batches"], fx["logs"]), start=1):
         model.feed_data({"LR": lr_img, "HR": hr_img})
         model.optimize_parameters(s)
         log = model.get_current_log()
+        log16 = None
+        if o16 is not None:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                log16 = o16.optimize_parameters(lr_img.cuda(), hr_img.cuda())
         for k, v in ref_log.items():
-            # relative tolerances only (no absolute floor).  Step 1 is a pure function of the inputs: 3e-2 (losses),
-            # 1e-1 for D_real / D_fake (means of TWO raw logits through five BatchNorms at batch 2).  Step 2 follows
-            # a GAN update at batch 2 (BatchNorm over 2 samples amplifies the bf16 rounding of step 1): D-side
-            # scalars 6e-2, the two-logit means 3.5e-1.
-            if k in ("D_real", "D_fake"):
-                tol = 1e-1 if s == 1 else 3.5e-1
-            else:
-                tol = 6e-2 if (s > 1 and k.startswith("l_d")) else 3e-2
+            # relative tolerances only (no absolute floor): 3e-2 at step 1 (a pure function of the inputs), 6e-2 for the
+            # D-side scalars at step 2 -- or 1.5 x the error of the reference's own bf16 path, whichever is larger:
+            # this shrunk config runs BatchNorm over TWO samples, which amplifies bf16 rounding (D_real / D_fake are
+            # means of two raw logits; measured reference-bf16 errors are printed beside ours)
+            tol = 6e-2 if (s > 1 and (k.startswith("l_d") or k.startswith("D_"))) else 3e-2
             e = abs(log[k] - v) / abs(v)
-            print("step %d %-14s reference % .6e  trainner_b200 % .6e  rel %.2e (tol %.1e)" % (s, k, v, log[k], e, tol))
-            assert e <= tol, (s, k, log[k], v)
+            e16 = abs(float(log16[k]) - v) / abs(v) if log16 is not None else 0.0
+            print("step %d %-14s reference % .6e  trainner_b200 % .6e  rel %.2e | reference-bf16 rel %.2e" %
+                  (s, k, v, log[k], e, e16))
+            if e > max(tol, 1.5 * e16):
+                problems.append((s, k, log[k], v, e, e16))
+    assert not problems, problems
     model.feed_data({"LR": fx["lr_test"], "HR": torch.zeros(fx["bs"], 3, fx["hr"], fx["hr"])})
     model.test()
     assert rel(model.fake_H, fx["sr_test"]) < 3e-2
     # Adam with lr 1e-4: every parameter moved by ~lr per step in the direction of its gradient sign;
     # compare the parameter sums recorded from the reference
+    # Per TENSOR (not a global sum): Adam's update after these steps is ~ -lr * sum of gradient signs per element; the
+    # fixture holds every tensor's sum, so the summed update of a tensor must agree with the reference's up to the
+    # sign flips of elements whose gradient is within bf16 rounding of zero (allowed: 2 % of the elements + 3 sqrt(n),
+    # each flip moves the sum by at most 2 lr per step).
     sd = model.netG.state_dict()
+    g0 = seeded(fx["g_shapes"], fx["g_seed"], fx["g_gain"])
+    lr, nsteps, bad = 1e-4, len(fx["batches"]), []
+    for k, (s_ref, _abs_ref) in fx["g_after"].items():
+        before = float(g0[k].double().sum())
+        d_ref, d_ours = s_ref - before, float(sd[k].double().sum()) - before
+        n = g0[k].numel()
+        if abs(d_ours - d_ref) > 2 * lr * nsteps * (0.02 * n + 3 * n ** 0.5):
+            bad.append((k, d_ours, d_ref, n))
+    assert not bad, bad[:10]
     tot_ref = sum(v[1] for v in fx["g_after"].values())
     tot = sum(float(v.double().abs().sum()) for v in sd.values())
     assert abs(tot - tot_ref) / tot_ref < 1e-3
@@ -298,10 +326,13 @@ def test_psnr_after_training_matches_reference_paths():
           "steps 200..%d: fp32 %.3f | reference bf16 %.3f | trainner_b200 %.3f dB" %
           (early + (len(late), steps, m32, m16, mb)))
     assert m32 > p_init + 10.0, "the synthetic task must be learnable (%.2f -> %.2f dB)" % (p_init, m32)
-    assert abs(early[2] - early[0]) <= 0.10, early
-    # 1.5 dB: the fp32 atomics of the split-K weight-gradient kernels make the CUDA trajectory vary from run to run
-    # on top of the chaos above (observed late-mean gaps over several runs: 0.3 .. 0.7 dB, either sign)
-    assert abs(mb - m32) <= max(1.5, 2.0 * abs(m16 - m32)), (m32, m16, mb)
+    # step 50, before round-off is amplified: within 0.03 dB of the fp32 run AND of the reference's bf16 run
+    # (measured 0.01-0.02 dB; the kernels are deterministic now, so this number is the same on every run)
+    assert abs(early[2] - early[0]) <= 0.03 and abs(early[2] - early[1]) <= 0.03, early
+    # late mean: Adam trajectories in different arithmetic diverge chaotically (fp32 vs the reference's own bf16 path
+    # differ by 0.2-0.4 dB in the mean, up to 4 dB at single checkpoints): no worse than 1.0 dB or twice the
+    # reference-bf16 gap
+    assert abs(mb - m32) <= max(1.0, 2.0 * abs(m16 - m32)), (m32, m16, mb)
 
 
 @pytest.mark.parametrize("shape", [(3, 12, 20, 2), (2, 16, 16, 1), (16, 64, 64, 23)])
@@ -341,3 +372,121 @@ def test_trunk_chain_matches_per_conv_flat_path(shape, monkeypatch):
     worst = max((rel(grads[1][k], grads[0][k]), k) for k in grads[0])
     print("chain vs flat: worst gradient rel-L2 %.3e (%s)" % worst)
     assert worst[0] < (2e-2 if nb <= 2 else 8e-2), worst
+
+
+def test_discriminator_backward_in_eval_mode():
+    """Discriminator_VGG.eval(): BatchNorm uses the running statistics (block.py:113-133), its gradient has no
+    batch-mean terms; parameters and input gradients vs the fp32 oracle with the reference-bf16 yardstick."""
+    from oracle import esrgan_oracle as O
+    from trainner_b200.architectures import discriminators
+    size = 32
+    fx = torch.load(os.path.join(GOLD, "modules.pt"))["disc_%d" % size]
+    sd = seeded(fx["shapes"], fx["seed"])
+    for k in sd:   # non-trivial running statistics
+        if k.endswith("running_mean"):
+            sd[k] = torch.randn(sd[k].shape, generator=torch.Generator().manual_seed(1)) * 0.1
+        if k.endswith("running_var"):
+            sd[k] = 0.5 + torch.rand(sd[k].shape, generator=torch.Generator().manual_seed(2))
+    net = discriminators.Discriminator_VGG(size, 3, 64).cuda()
+    net.load_state_dict(sd)
+    net.eval()
+    x = fx["x"]
+    xc = x.cuda().requires_grad_(True)
+    y = net(xc)
+    dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(6))
+
+    def oracle(autocast):
+        p = OrderedDict((k, (v.clone().cuda().requires_grad_(True) if (v.is_floating_point() and "running" not in k)
+                             else v.clone().cuda())) for k, v in sd.items())
+        xo = x.cuda().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            yo = O.discriminator_vgg_forward(p, xo, size, training=False)
+        yo.float().backward(dy.cuda())
+        return yo.detach().float(), xo.grad.float(), OrderedDict((k, v.grad.float()) for k, v in p.items() if v.requires_grad)
+
+    y32, dx32, g32 = oracle(False)
+    y16, dx16, g16 = oracle(True)
+    assert rel(y, y32) <= max(1e-2, 1.25 * rel(y16, y32))
+    y.backward(dy.cuda())
+    assert rel(xc.grad, dx32) <= max(0.03, 1.25 * rel(dx16, dx32)), (rel(xc.grad, dx32), rel(dx16, dx32))
+    bad = []
+    for k, p in net.named_parameters():
+        e, e_ref = rel(p.grad, g32[k]), rel(g16[k], g32[k])
+        if e > max(0.03, 1.25 * e_ref):
+            bad.append((k, e, e_ref))
+    assert not bad, bad[:10]
+    for k, v in net.state_dict().items():   # eval mode must not touch the running statistics
+        if "running" in k:
+            assert torch.equal(v.cpu(), sd[k]), k
+
+
+def test_feature_extractor_relu_tap_gradient(tmp_path):
+    """listen_list = ['relu5_4'] (a ReLU OUTPUT tap, perceptual.py:201-214): the incoming gradient is wrt the
+    activation, so the last layer's own ReLU mask must be applied before the dgrad chain."""
+    from oracle import esrgan_oracle as O
+    import torchvision
+    from ref_harness import seeded_state
+    from trainner_b200.architectures import perceptual
+    tv_shapes = OrderedDict((k, tuple(v.shape)) for k, v in torchvision.models.vgg19(weights=None).state_dict().items())
+    tv_sd = seeded_state(tv_shapes, 7)
+    ck = tmp_path / "vgg19.pth"
+    torch.save(tv_sd, ck)
+    net = perceptual.FeatureExtractor(listen_list=["relu5_4"], load_path=str(ck)).cuda()
+    x = torch.rand(2, 3, 48, 64, generator=torch.Generator().manual_seed(3))
+    xc = x.cuda().requires_grad_(True)
+    f = net(xc)["relu5_4"]
+    fsd = OrderedDict((k, v.cuda()) for k, v in O.torchvision_vgg_to_feature_net(tv_sd).items())
+    tgt = torch.randn(f.shape, generator=torch.Generator().manual_seed(7)).cuda()
+
+    def oracle(autocast):
+        xo = x.cuda().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            fo = torch.relu(O.vgg19_features(fsd, xo)["conv5_4"])
+            loss = torch.nn.functional.l1_loss(fo, tgt)
+        loss.backward()
+        return fo.detach().float(), xo.grad.float()
+
+    (f32, dx32), (f16, dx16) = oracle(False), oracle(True)
+    assert rel(f, f32) <= max(2e-2, 1.25 * rel(f16, f32))
+    from trainner_b200.losses import L1Loss
+    L1Loss()(f, tgt.to(f.dtype)).backward()
+    assert rel(xc.grad, dx32) <= max(0.05, 1.25 * rel(dx16, dx32)), (rel(xc.grad, dx32), rel(dx16, dx32))
+
+
+def test_training_steps_are_bit_reproducible(tmp_path):
+    """No float atomics anywhere in the library (ordered split-K slabs, last-block sums): two runs of the same
+    8 GAN steps from the same weights give bit-identical parameters, BatchNorm statistics and losses."""
+    import torchvision
+    from trainner_b200.models.sr_model import create_model
+    vgg_path = str(tmp_path / "vgg19.pth")
+    torch.manual_seed(5)
+    torch.save(torchvision.models.vgg19(weights=None).state_dict(), vgg_path)
+    opt = {"model": "sr", "scale": 4, "is_train": True, "datasets": {"train": {"crop_size": 64}},
+           "network_G": {"type": "esrgan", "nb": 3, "nf": 64, "gaussian": False, "init_scale": 0.3},
+           "network_D": {"type": "discriminator_vgg"},
+           "train": {"pixel_weight": 1e-2, "feature_weight": 1.0, "gan_weight": 5e-3, "gan_type": "vanilla",
+                     "lr_G": 1e-4, "lr_D": 1e-4, "perceptual_opt": {"pretrained_path": vgg_path}}}
+    runs = []
+    init = None
+    for _ in range(2):
+        torch.manual_seed(0)
+        model = create_model(opt)
+        if init is None:
+            init = (OrderedDict((k, v.clone()) for k, v in model.netG.state_dict().items()),
+                    OrderedDict((k, v.clone()) for k, v in model.netD.state_dict().items()))
+        model.netG.load_state_dict(init[0])
+        model.netD.load_state_dict(init[1])
+        logs = []
+        for s in range(1, 9):
+            g = torch.Generator().manual_seed(100 + s)
+            model.feed_data({"LR": torch.rand(6, 3, 16, 16, generator=g), "HR": torch.rand(6, 3, 64, 64, generator=g)})
+            model.optimize_parameters(s)
+            logs.append(model.get_current_log())
+        model.synchronize()
+        runs.append((logs, OrderedDict((k, v.clone()) for k, v in model.netG.state_dict().items()),
+                     OrderedDict((k, v.clone()) for k, v in model.netD.state_dict().items())))
+    assert runs[0][0] == runs[1][0], "losses differ between two identical runs"
+    for which in (1, 2):
+        for k, v in runs[0][which].items():
+            assert torch.equal(v, runs[1][which][k]), "run-to-run difference in %s" % k
+    assert any(not torch.equal(v, init[0][k]) for k, v in runs[0][1].items())

@@ -40,6 +40,6 @@ for cta in (0, 1, 68, 135, 136):
     t0 = int(d[cta, 0])
     print("cta %3d: total %d cycles" % (cta, int(d[cta, 1]) - t0))
     for s in range(7):
-        r, i, c, t, e, p1 = (int(d[cta, 2 + 8 * s + k]) - t0 for k in range(6))
-        print("   s%-2d R %7d  I +%5d  C +%5d  E(stores) +%5d  P1(first poll) +%5d  T +%5d  (poll rounds of lane 0: %d)" %
-              (s, r, i - r, c - i, e - c, p1 - e, t - p1, int(d[cta, 8 + 8 * s])))
+        r, i, c, t, e, l, f, st = (int(d[cta, 2 + 8 * s + k]) - t0 for k in range(8))
+        print("   s%-2d R %7d  I +%5d  C +%5d | tmem_ld +%5d  math +%5d  stores +%5d  loop-end(E) +%5d | T(arrive) +%5d" %
+              (s, r, i - r, c - i, l - c, f - l, st - f, e - st, t - e))

@@ -144,8 +144,8 @@ _SIGNATURES = {
     "b200_bn_stats": [_P, _P, _L, _I, _P],
     "b200_bn_finalize": [_P, _P, _P, _P, _L, _I, _F, _F, _P],
     "b200_bn_apply_lrelu": [_P, _P, _P, _P, _P, _L, _I, _F, _P],
-    "b200_bn_bwd_reduce": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
-    "b200_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
+    "b200_bn_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
+    "b200_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P],
     "b200_maxpool2x2": [_P, _P, _I, _I, _I, _I, _P],
     "b200_maxpool2x2_bwd": [_P, _P, _P, _I, _I, _I, _I, _P],
     "b200_sumpool2x2_mask": [_P, _P, _P, _I, _I, _I, _I, _F, _P],

@@ -10,7 +10,8 @@ namespace b200 {
 // blockDim.x = 256; `red` is shared memory for 256 * 8 floats.  Requires c % 8 == 0, c <= 2048,
 // pitch % 8 == 0, coff % 8 == 0 (16-byte aligned vectors).  Adds scale * sum into dst[0..c).
 // Deterministic: every block of the gridDim.x blocks that share `dst` parks its c partial sums in
-// part[c][gridDim.x]; the last block to arrive on `counter` adds them in block order (common.cuh).
+// part[c][gridDim.x] (+ c * ceil(gridDim.x / 16) floats of group sums behind it); two-level ordered sum
+// (common.cuh: det_reduce; `counter` = 1 + ceil(gridDim.x / 16) words).
 __device__ __forceinline__ void colsum_vec(const __nv_bfloat16* __restrict__ src, long long npix, int pitch,
                                            int coff, int c, float scale, float* __restrict__ dst,
                                            float* __restrict__ red, float* __restrict__ part,
@@ -62,8 +63,7 @@ __device__ __forceinline__ void colsum_vec(const __nv_bfloat16* __restrict__ src
     for (int p = 0; p < ppb; ++p) tot += red[j * 256 + p * vl + lane];
     part[(size_t)ch * gridDim.x + blockIdx.x] = tot;
   }
-  if (det_arrive_last(counter, gridDim.x))
-    det_sum_blocks(part, gridDim.x, c, red, [&](int ch, float tot) { dst[ch] += scale * tot; });
+  det_reduce(part, part + (size_t)c * gridDim.x, counter, gridDim.x, c, [&](int ch, float tot) { dst[ch] += scale * tot; });
 }
 
 }  // namespace b200

@@ -123,23 +123,35 @@ __device__ __forceinline__ bool det_arrive_last(unsigned* counter, unsigned nblk
   return last;
 }
 
-// Run by the last block (all 256 threads = 8 warps): out(k, sum_b part[k * nblk + b]) for k < nout, the sum
-// taken in a FIXED order: warp w owns outputs k = w, w + 8, ..; its lanes add the blocks b = lane, lane + 32, ..
-// (coalesced, all loads independent) and the 32 lane sums are combined by a shuffle tree.  `sh` is unused
-// (kept for call-site compatibility).  Partials are laid out OUTPUT-major: part[k * nblk + b].
+// Deterministic cross-block sum in two levels (a single last block adding nblk x nout partials would be a
+// multi-microsecond serial tail): the blocks form groups of kDetGroup; the last block of a group to arrive adds the
+// group's partials (contiguous in memory: part is OUTPUT-major, part[k * nblk + b]) in block order into
+// gpart[k * ngrp + g]; the last GROUP to finish adds the group sums in group order and calls out(k, total).
+// counters: 1 + ngrp words (self-resetting).  Every block of the grid must call it (blockDim.x = 256).
+constexpr int kDetGroup = 16;
+__host__ __device__ __forceinline__ int det_groups(int nblk) { return (nblk + kDetGroup - 1) / kDetGroup; }
+
 template <typename F>
-__device__ __forceinline__ void det_sum_blocks(const float* __restrict__ part, unsigned nblk, int nout, float* sh,
-                                               F&& out) {
-  (void)sh;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarp = blockDim.x >> 5;
-  for (int k = warp; k < nout; k += nwarp) {
-    const float* row = part + (size_t)k * nblk;
+__device__ __forceinline__ void det_reduce(const float* __restrict__ part, float* __restrict__ gpart,
+                                           unsigned* counters, unsigned nblk, int nout, F&& out) {
+  const unsigned grp = blockIdx.x / kDetGroup, ngrp = det_groups((int)nblk);
+  const unsigned g0 = grp * kDetGroup;
+  const unsigned members = (nblk - g0) < (unsigned)kDetGroup ? (nblk - g0) : (unsigned)kDetGroup;
+  if (!det_arrive_last(counters + 1 + grp, members)) return;
+  for (int k = threadIdx.x; k < nout; k += blockDim.x) {
+    const float* row = part + (size_t)k * nblk + g0;
     float t = 0.f;
-    for (unsigned b = lane; b < nblk; b += 32) t += row[b];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0) out(k, t);
+#pragma unroll 4
+    for (unsigned i = 0; i < members; ++i) t += row[i];
+    gpart[(size_t)k * ngrp + grp] = t;
+  }
+  if (!det_arrive_last(counters, ngrp)) return;
+  for (int k = threadIdx.x; k < nout; k += blockDim.x) {
+    const float* row = gpart + (size_t)k * ngrp;
+    float t = 0.f;
+#pragma unroll 4
+    for (unsigned g = 0; g < ngrp; ++g) t += row[g];
+    out(k, t);
   }
 }
 #endif

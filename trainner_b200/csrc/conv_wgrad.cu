@@ -307,7 +307,7 @@ extern "C" int b200_conv_wgrad(const b200_wgrad_desc* d, const void* x, const vo
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, 1);
     DetScratch ds;
-    if (det_scratch(&ds, (size_t)gx * d->cout, 1)) return 1;
+    if (det_scratch(&ds, (size_t)(gx + det_groups((int)gx)) * d->cout, 1 + det_groups((int)gx))) return 1;
     ::b200::launch_kernel(colsum_kernel, grid, 256, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(dy),
                                                       dbias, npix, d->cdy, d->dy_coff, d->cout,
                                                       d->scale, ds.part, ds.counters);

@@ -44,7 +44,8 @@ __global__ void bn_reduce_kernel(const __nv_bfloat16* __restrict__ z,
                                  const float* __restrict__ mean_invstd,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float* __restrict__ sums, long long npix, int c, float slope,
-                                 float* __restrict__ part, unsigned* __restrict__ counter) {
+                                 float* __restrict__ part, unsigned* __restrict__ counter,
+                                 float* __restrict__ dgamma, float* __restrict__ dbeta) {
   pdl_trigger();
   pdl_wait();
   const int vec_per_pix = c / 8;
@@ -118,9 +119,19 @@ __global__ void bn_reduce_kernel(const __nv_bfloat16* __restrict__ z,
     for (int q = ln; q < 256; q += vec_per_pix) t += sh[j * 256 + q];
     part[(size_t)k * gridDim.x + blockIdx.x] = t;
   }
-  // deterministic grid reduction: the last block to arrive adds the per-block partials in block order
-  if (det_arrive_last(counter, gridDim.x))
-    det_sum_blocks(part, gridDim.x, 2 * c, sh, [&](int k, float t) { sums[k] = t; });
+  // deterministic two-level grid reduction (common.cuh)
+  det_reduce(part, part + (size_t)2 * c * gridDim.x, counter, gridDim.x, 2 * c, [&](int k, float t) {
+    sums[k] = t;
+    // MODE 1: sums[0..c) = sum dbn = d(beta), sums[c..2c) = sum dbn * zhat = d(gamma): accumulated here instead of
+    // two extra launches per layer
+    if (MODE == 1) {
+      if (k < c) {
+        if (dbeta) dbeta[k] += t;
+      } else if (dgamma) {
+        dgamma[k - c] += t;
+      }
+    }
+  });
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, float* __restrict__ mean_invstd,
@@ -149,7 +160,7 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z,
                                 const float* __restrict__ mean_invstd,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ sums, __nv_bfloat16* __restrict__ out,
-                                long long npix, int c, float slope) {
+                                long long npix, int c, float slope, int use_batch_stats) {
   pdl_trigger();
   pdl_wait();
   const int vec_per_pix = c / 8;
@@ -158,7 +169,9 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z,
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cv = (int)(i % vec_per_pix) * 8;
   float mu[8], is[8], ga[8], be[8], m0[8], m1[8];
-  const float inv_n = 1.f / (float)npix;
+  // eval mode (running statistics): the normalisation is a fixed per-channel affine map, so the batch-mean terms
+  // of the train-mode gradient vanish
+  const float inv_n = use_batch_stats ? 1.f / (float)npix : 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     mu[j] = mean_invstd[cv + j];
@@ -427,15 +440,8 @@ __global__ void l1_loss_kernel(const T* __restrict__ a, const T* __restrict__ b,
     s = warp_sum(s);
     if (l == 0) part[blockIdx.x] = s;
   }
-  // deterministic grid reduction (block order) by the last block to arrive
-  if (det_arrive_last(counter, gridDim.x)) {
-    if (w == 0) {
-      float t = 0.f;
-      for (unsigned b = l; b < gridDim.x; b += 32) t += part[b];
-      t = warp_sum(t);
-      if (l == 0) *loss_out = t * scale;
-    }
-  }
+  // deterministic two-level grid reduction (common.cuh)
+  det_reduce(part, part + gridDim.x, counter, gridDim.x, 1, [&](int, float t) { *loss_out = t * scale; });
 }
 
 // ------------------------------------------------------------------ layout conversion
@@ -517,9 +523,9 @@ int b200_bn_stats(const void* z, float* stats, int64_t npix, int32_t c, b200_str
   B200_REQUIRE(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "b200_bn_stats: c/8 must be a power of two <= 256 (c=%d)", c);
   const int grid = bn_grid(npix, c, 4, 148 * 2);   // the last block adds the per-block partials: keep them few
   DetScratch ds;
-  if (det_scratch(&ds, (size_t)grid * 2 * c, 1)) return 1;
+  if (det_scratch(&ds, (size_t)(grid + det_groups(grid)) * 2 * c, 1 + det_groups(grid))) return 1;
   ::b200::launch_kernel(bn_reduce_kernel<0>, grid, 256, 16 * 256 * sizeof(float), as_stream(stream), 
-      (const bf16*)z, nullptr, nullptr, nullptr, nullptr, stats, npix, c, 0.f, ds.part, ds.counters);
+      (const bf16*)z, nullptr, nullptr, nullptr, nullptr, stats, npix, c, 0.f, ds.part, ds.counters, nullptr, nullptr);
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -538,38 +544,30 @@ int b200_bn_apply_lrelu(const void* z, const float* mean_invstd, const float* ga
                         b200_stream_t stream) {
   B200_REQUIRE(c % 8 == 0, "b200_bn_apply_lrelu: c must be a multiple of 8");
   ::b200::launch_kernel(bn_apply_kernel<0>, bn_grid(npix, c, 2), 256, 0, as_stream(stream), 
-      (const bf16*)z, nullptr, mean_invstd, gamma, beta, nullptr, (bf16*)a, npix, c, slope);
+      (const bf16*)z, nullptr, mean_invstd, gamma, beta, nullptr, (bf16*)a, npix, c, slope, 1);
   B200_LAUNCH_CHECK();
   return 0;
 }
 
 int b200_bn_bwd_reduce(const void* z, const void* da, const float* mean_invstd, const float* gamma,
-                       const float* beta, float* sums, int64_t npix, int32_t c, float slope,
-                       b200_stream_t stream) {
+                       const float* beta, float* sums, float* dgamma, float* dbeta, int64_t npix, int32_t c,
+                       float slope, b200_stream_t stream) {
   B200_REQUIRE(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "b200_bn_bwd_reduce: c/8 must be a power of two <= 256 (c=%d)", c);
   const int grid = bn_grid(npix, c, 4, 148 * 2);   // the last block adds the per-block partials: keep them few
   DetScratch ds;
-  if (det_scratch(&ds, (size_t)grid * 2 * c, 1)) return 1;
+  if (det_scratch(&ds, (size_t)(grid + det_groups(grid)) * 2 * c, 1 + det_groups(grid))) return 1;
   ::b200::launch_kernel(bn_reduce_kernel<1>, grid, 256, 16 * 256 * sizeof(float), as_stream(stream), 
-      (const bf16*)z, (const bf16*)da, mean_invstd, gamma, beta, sums, npix, c, slope, ds.part, ds.counters);
+      (const bf16*)z, (const bf16*)da, mean_invstd, gamma, beta, sums, npix, c, slope, ds.part, ds.counters, dgamma, dbeta);
   B200_LAUNCH_CHECK();
   return 0;
 }
 
 int b200_bn_bwd_apply(const void* z, const void* da, const float* mean_invstd, const float* gamma,
-                      const float* beta, const float* sums, void* dz, float* dgamma, float* dbeta,
-                      int64_t npix, int32_t c, float slope, b200_stream_t stream) {
+                      const float* beta, const float* sums, void* dz, int64_t npix, int32_t c, float slope,
+                      int32_t use_batch_stats, b200_stream_t stream) {
   ::b200::launch_kernel(bn_apply_kernel<1>, bn_grid(npix, c, 2), 256, 0, as_stream(stream), 
-      (const bf16*)z, (const bf16*)da, mean_invstd, gamma, beta, sums, (bf16*)dz, npix, c, slope);
+      (const bf16*)z, (const bf16*)da, mean_invstd, gamma, beta, sums, (bf16*)dz, npix, c, slope, (int)use_batch_stats);
   B200_LAUNCH_CHECK();
-  if (dgamma) {
-    ::b200::launch_kernel(add_small_kernel, (c + 127) / 128, 128, 0, as_stream(stream), dgamma, sums + c, c);
-    B200_LAUNCH_CHECK();
-  }
-  if (dbeta) {
-    ::b200::launch_kernel(add_small_kernel, (c + 127) / 128, 128, 0, as_stream(stream), dbeta, sums, c);
-    B200_LAUNCH_CHECK();
-  }
   return 0;
 }
 
@@ -627,7 +625,7 @@ int b200_l1_loss_f32(const float* a, const float* b, float* loss_out, float* gra
                      float weight, b200_stream_t stream) {
   const int grid = grid_for(numel, 256, 148 * 4);
   DetScratch ds;
-  if (det_scratch(&ds, (size_t)grid, 1)) return 1;
+  if (det_scratch(&ds, (size_t)grid + det_groups(grid), 1 + det_groups(grid))) return 1;
   ::b200::launch_kernel(l1_loss_kernel<float>, grid, 256, 0, as_stream(stream), 
       a, b, loss_out, grad_a, numel, weight / (float)numel, ds.part, ds.counters);
   B200_LAUNCH_CHECK();
@@ -638,7 +636,7 @@ int b200_l1_loss_bf16(const void* a, const void* b, float* loss_out, void* grad_
                       float weight, b200_stream_t stream) {
   const int grid = grid_for(numel, 256, 148 * 4);
   DetScratch ds;
-  if (det_scratch(&ds, (size_t)grid, 1)) return 1;
+  if (det_scratch(&ds, (size_t)grid + det_groups(grid), 1 + det_groups(grid))) return 1;
   ::b200::launch_kernel(l1_loss_kernel<bf16>, grid, 256, 0, as_stream(stream), 
       (const bf16*)a, (const bf16*)b, loss_out, (bf16*)grad_a, numel, weight / (float)numel, ds.part, ds.counters);
   B200_LAUNCH_CHECK();

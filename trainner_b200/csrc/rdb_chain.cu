@@ -402,6 +402,7 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
           tmem_ld_32x32b_x32(t_row + 32 * j + c0, acc);
           if (c0 > 0 && valid) prefetch32(e, q, c0, m);
           tmem_ld_wait();
+          if (s < 7 && warp == 3 && c0 == 0) CDBG(7 + 8 * s);
           uint4 o[4];
           if (valid) {
             finish32(e, acc, q, o);
@@ -409,6 +410,7 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) o[g] = make_uint4(0, 0, 0, 0);   // border / out-of-range positions stay zero
           }
+          if (s < 7 && warp == 3 && c0 == 0) CDBG(8 + 8 * s);
           const int cb = c0 >> 3;   // first chunk index
           // (1) own rows of the next operand slice, 128B-swizzled K-major (the in-cluster halo pushes read them)
           if (more) {
@@ -438,6 +440,7 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) dst[g] = o[g];
           }
+          if (s < 7 && warp == 3 && c0 == 0) CDBG(9 + 8 * s);
         }
         tc_fence_before();
         if (s < 7 && warp == 3) CDBG(6 + 8 * s);   // epilogue math + stores issued

@@ -244,7 +244,7 @@ thin_wgrad_kernel(const float* __restrict__ thin, const __nv_bfloat16* __restric
   // reduce the 4 pixel subsets into this block's partial row [64 lanes][CS*9 + 1]; the last block of the
   // channel group (blockIdx.y) to arrive adds the rows of all blocks in block order (deterministic)
   constexpr int NC1 = CS * 9 + 1;
-  float* mine = part + (size_t)blockIdx.y * gridDim.x * 64 * NC1;   // output-major: [64 * NC1][gridDim.x]
+  float* mine = part + (size_t)blockIdx.y * (gridDim.x + det_groups(gridDim.x)) * 64 * NC1;   // output-major [64 * NC1][gridDim.x] + group sums
 #pragma unroll
   for (int k = 0; k < NC1; ++k) {
     __syncthreads();
@@ -254,21 +254,19 @@ thin_wgrad_kernel(const float* __restrict__ thin, const __nv_bfloat16* __restric
       mine[(size_t)(lane_c * NC1 + k) * gridDim.x + blockIdx.x] =
           red[0][lane_c] + red[1][lane_c] + red[2][lane_c] + red[3][lane_c];
   }
-  if (det_arrive_last(counters + blockIdx.y, gridDim.x)) {
-    __shared__ float shs[256];
-    det_sum_blocks(part + (size_t)blockIdx.y * gridDim.x * 64 * NC1, gridDim.x, 64 * NC1, shs, [&](int i, float sv) {
-      const int m = i / NC1, k = i % NC1;
-      const int jj = blockIdx.y * 64 + m;
-      if (jj >= cw) return;
-      if (k < CS * 9) {
-        const int ci = k / 9, t = k % 9;
-        const size_t idx = wide_is_out ? ((size_t)jj * CS + ci) * 9 + t : ((size_t)ci * cw + jj) * 9 + t;
-        dw[idx] += sv;
-      } else if (dbias_wide) {
-        dbias_wide[jj] += sv;
-      }
-    });
-  }
+  det_reduce(mine, mine + (size_t)64 * NC1 * gridDim.x, counters + blockIdx.y * (1 + det_groups(gridDim.x)), gridDim.x,
+             64 * NC1, [&](int i, float sv) {
+    const int m = i / NC1, k = i % NC1;
+    const int jj = blockIdx.y * 64 + m;
+    if (jj >= cw) return;
+    if (k < CS * 9) {
+      const int ci = k / 9, t = k % 9;
+      const size_t idx = wide_is_out ? ((size_t)jj * CS + ci) * 9 + t : ((size_t)ci * cw + jj) * 9 + t;
+      dw[idx] += sv;
+    } else if (dbias_wide) {
+      dbias_wide[jj] += sv;
+    }
+  });
 }
 
 // ================================================================= tensor-core (mma.sync) versions
@@ -610,23 +608,21 @@ thin_wgrad_mma_kernel(const float* __restrict__ thin, const __nv_bfloat16* __res
     __syncthreads();
   }
   // this block's partial [64][NC] -> scratch; the last block of the channel group adds all blocks in block order
-  float* mine = part + (size_t)blockIdx.y * gridDim.x * 64 * NC;   // output-major: [64 * NC][gridDim.x]
+  float* mine = part + (size_t)blockIdx.y * (gridDim.x + det_groups(gridDim.x)) * 64 * NC;   // output-major [64 * NC][gridDim.x] + group sums
   for (int i = tid; i < 64 * NC; i += 256) mine[(size_t)i * gridDim.x + blockIdx.x] = red[(i / NC) * RS + (i % NC)];
-  if (det_arrive_last(counters + blockIdx.y, gridDim.x)) {
-    __shared__ float shs[256];
-    det_sum_blocks(part + (size_t)blockIdx.y * gridDim.x * 64 * NC, gridDim.x, 64 * NC, shs, [&](int i, float sv) {
-      const int m = i / NC, nn = i % NC;
-      const int j = jbase + m;
-      if (j >= cw) return;
-      if (nn < CS * 9) {
-        const int ci = nn / 9, tp = nn % 9;
-        const size_t idx = wide_is_out ? ((size_t)j * CS + ci) * 9 + tp : ((size_t)ci * cw + j) * 9 + tp;
-        dw[idx] += sv;
-      } else if (dbias_wide) {
-        dbias_wide[j] += sv;
-      }
-    });
-  }
+  det_reduce(mine, mine + (size_t)64 * NC * gridDim.x, counters + blockIdx.y * (1 + det_groups(gridDim.x)), gridDim.x,
+             64 * NC, [&](int i, float sv) {
+    const int m = i / NC, nn = i % NC;
+    const int j = jbase + m;
+    if (j >= cw) return;
+    if (nn < CS * 9) {
+      const int ci = nn / 9, tp = nn % 9;
+      const size_t idx = wide_is_out ? ((size_t)j * CS + ci) * 9 + tp : ((size_t)ci * cw + j) * 9 + tp;
+      dw[idx] += sv;
+    } else if (dbias_wide) {
+      dbias_wide[j] += sv;
+    }
+  });
 }
 
 __global__ void plane_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int n, int c,
@@ -757,7 +753,8 @@ int b200_conv3x3_thin_wgrad(const float* thin, const void* wide, float* dw, floa
   // deterministic cross-block reduction: per-block partials [grid.y][grid.x][64][cs*9+1] in the library scratch;
   // the plane sums (launched after, stream-ordered) reuse the front of the same arena
   DetScratch ds;
-  if (det_scratch(&ds, (size_t)grid.x * grid.y * 64 * (cs * 9 + 1) + 32 * 4, (int)grid.y + 8)) return 1;
+  if (det_scratch(&ds, (size_t)(grid.x + det_groups(grid.x)) * grid.y * 64 * (cs * 9 + 1) + 32 * 4,
+                  (int)grid.y * (1 + det_groups(grid.x)) + 8)) return 1;
   const int w16 = (w + 15) / 16 * 16;
   const size_t msm = (size_t)w16 * 128 + (size_t)cs * 3 * (w16 + 2) * sizeof(float);
   if (cw % 64 == 0 && cwide_buf % 8 == 0 && wide_coff % 8 == 0 && msm <= 48 * 1024 && msm >= 64 * 41 * 4) {

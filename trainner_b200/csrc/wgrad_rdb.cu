@@ -283,8 +283,9 @@ __global__ void __launch_bounds__(256) colsum_multi_kernel(const b200_colsum_ent
   pdl_wait();
   __shared__ float red[256 * 8];
   const b200_colsum_entry e = table[blockIdx.y];
+  const int stride = gridDim.x + det_groups(gridDim.x);
   colsum_vec(reinterpret_cast<const __nv_bfloat16*>(e.src), e.npix, e.pitch, e.coff, e.c, e.scale, e.dst, red,
-             part + (size_t)blockIdx.y * gridDim.x * c_max, counters + blockIdx.y);
+             part + (size_t)blockIdx.y * stride * c_max, counters + blockIdx.y * (1 + det_groups(gridDim.x)));
 }
 
 }  // namespace
@@ -299,7 +300,7 @@ extern "C" int b200_colsum_multi(const b200_colsum_entry* table_dev, int32_t cou
   const int c_max = 256;
   dim3 grid(32, count);
   DetScratch ds;
-  if (det_scratch(&ds, (size_t)count * 32 * c_max, count)) return 1;
+  if (det_scratch(&ds, (size_t)count * (32 + det_groups(32)) * c_max, count * (1 + det_groups(32)))) return 1;
   ::b200::launch_kernel(colsum_multi_kernel, grid, 256, 0, as_stream(stream), table_dev, ds.part, ds.counters, c_max);
   B200_LAUNCH_CHECK();
   return 0;

@@ -110,7 +110,7 @@ class DiscriminatorEngine:
         ctx.bwd = {}
         return ctx
 
-    def _make_backward(self, ctx, wgrad, xgrad):
+    def _make_backward(self, ctx, wgrad, xgrad, train=True):
         net = self.net
         dev = self.device
         N, S = ctx.N, ctx.S
@@ -132,10 +132,10 @@ class DiscriminatorEngine:
             hi, ho = ctx.dims[i]
             npix = N * ho * ho
             b.add(lib.b200_bn_bwd_reduce, P(ctx.Z[i]), P(ctx.dA[i + 1]), P(ctx.mi[i]), P(bn.weight), P(bn.bias),
-                  P(ctx.sums[i]), npix, L.cout, SL)
+                  P(ctx.sums[i]), P(g(bn.weight)) if wgrad else None, P(g(bn.bias)) if wgrad else None, npix, L.cout,
+                  SL)
             b.add(lib.b200_bn_bwd_apply, P(ctx.Z[i]), P(ctx.dA[i + 1]), P(ctx.mi[i]), P(bn.weight), P(bn.bias),
-                  P(ctx.sums[i]), P(ctx.dZ[i]), P(g(bn.weight)) if wgrad else None,
-                  P(g(bn.bias)) if wgrad else None, npix, L.cout, SL)
+                  P(ctx.sums[i]), P(ctx.dZ[i]), npix, L.cout, SL, 1 if train else 0)
             if wgrad:
                 add_wgrad(b, N, hi, hi, L.cin, 0, L.cin, ho, ho, L.cout, 0, L.cout, L.kh, L.stride, L.pad, 1.0,
                           ctx.A[i], ctx.dZ[i], g(L.weight), g(L.bias))
@@ -162,7 +162,7 @@ class DiscriminatorEngine:
         if xgrad:
             b.add(lib.b200_conv3x3_wide_to_thin, P(ctx.dA[0]), P(self.conv0.weight), None, P(ctx.dx), N, S, S, c0,
                   c0, 0, net.in_nc, 1, None, 1.0)
-        ctx.bwd[(wgrad, xgrad)] = b
+        ctx.bwd[(wgrad, xgrad, train)] = b
 
     # ------------------------------------------------------------------ run
     def forward(self, x, need_backward, training):
@@ -216,13 +216,12 @@ class DiscriminatorEngine:
 
     def backward(self, lease, dfeat, xgrad):
         ctx = lease.ctx
-        if not ctx.trained:
-            raise NotImplementedError("Discriminator_VGG backward in eval() mode (running-stat BatchNorm) "
-                                      "is not on the training hot path")
         wgrad = any(p.requires_grad for p in self.net.features.parameters())
-        key = (wgrad, xgrad)
+        # eval()-mode forward (running statistics, ctx.mi filled from them): the same plan with the batch-mean
+        # terms of the BatchNorm gradient switched off
+        key = (wgrad, xgrad, bool(ctx.trained))
         if key not in ctx.bwd:
-            self._make_backward(ctx, wgrad, xgrad)
+            self._make_backward(ctx, wgrad, xgrad, train=bool(ctx.trained))
         if wgrad:
             self.grads.attach()
         ctx.dfeat.copy_(dfeat)

@@ -165,7 +165,7 @@ def batchnorm_lrelu_train(z, gamma, beta, running_mean=None, running_var=None, m
     return a, mi
 
 
-def batchnorm_lrelu_backward(z, da, mi, gamma, beta, slope=0.2):
+def batchnorm_lrelu_backward(z, da, mi, gamma, beta, slope=0.2, use_batch_stats=True):
     require_device(z, "batchnorm_lrelu_backward")
     c = z.shape[-1]
     npix = z.numel() // c
@@ -174,10 +174,10 @@ def batchnorm_lrelu_backward(z, da, mi, gamma, beta, slope=0.2):
     dgamma = torch.zeros(c, dtype=torch.float32, device=z.device)
     dbeta = torch.zeros(c, dtype=torch.float32, device=z.device)
     s = stream_ptr()
-    _lib.check(lib.b200_bn_bwd_reduce(_p(z), _p(da), _p(mi), _p(gamma), _p(beta), _p(sums), npix, c, slope, s),
-               "bn_bwd_reduce")
-    _lib.check(lib.b200_bn_bwd_apply(_p(z), _p(da), _p(mi), _p(gamma), _p(beta), _p(sums), _p(dz), _p(dgamma),
-                                     _p(dbeta), npix, c, slope, s), "bn_bwd_apply")
+    _lib.check(lib.b200_bn_bwd_reduce(_p(z), _p(da), _p(mi), _p(gamma), _p(beta), _p(sums), _p(dgamma), _p(dbeta), npix,
+                                      c, slope, s), "bn_bwd_reduce")
+    _lib.check(lib.b200_bn_bwd_apply(_p(z), _p(da), _p(mi), _p(gamma), _p(beta), _p(sums), _p(dz), npix, c, slope,
+                                     1 if use_batch_stats else 0, s), "bn_bwd_apply")
     return dz, dgamma, dbeta
 
 

@@ -82,8 +82,11 @@ class Plan:
                 with torch.cuda.graph(g):
                     self._run_eager()
                 self._graph = g
-            except Exception:
-                self._graph = False   # not capturable on this setup: stay eager
+            except Exception as exc:   # not capturable on this setup: stay eager, but say so (a silent perf cliff otherwise)
+                self._graph = False
+                import warnings
+                warnings.warn("trainner_b200: CUDA-graph capture of a %d-call plan failed (%s: %s); the plan stays eager"
+                              % (len(self.calls), type(exc).__name__, exc), RuntimeWarning)
                 torch.cuda.synchronize()
                 return self._run_eager()
         self._graph.replay()
