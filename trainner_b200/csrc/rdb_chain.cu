@@ -31,6 +31,9 @@
 // trunk (block.py:184-192) and their autograd input gradients.
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -391,7 +394,14 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
           else mbar_arrive(&slice_ready[tile][pn]);
         }
         EpiPre q;
-        if (valid) prefetch32(e, q, 0, m);
+        if (valid) {
+          prefetch32(e, q, 0, m);
+          if (j == 4) {   // second 32-channel half of the 64-channel stage: warm L1 now, the loads are issued after the first half
+            if (e.res1) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const __nv_bfloat16*>(e.res1) + m * e.res1_c + e.res1_coff + 32));
+            if (e.res2) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const __nv_bfloat16*>(e.res2) + m * e.res2_c + e.res2_coff + 32));
+            if (e.mask) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const __nv_bfloat16*>(e.mask) + m * e.mask_c + e.mask_coff + 32));
+          }
+        }
         mbar_wait(&acc_ready[tile], acc_ph);
         acc_ph ^= 1;
         tc_fence_after();
@@ -630,7 +640,20 @@ extern "C" int b200_rdb_chain(const b200_chain_desc* d, const void* x0, const vo
     if (cs_max > 8) cs_max = 8;
   }
   int cs = 1, grid = n_cta;
-  for (int c = cs_max; c >= 2; c >>= 1) {
+  // decided once per grid size (the occupancy query must not run inside a stream capture)
+  static std::mutex cs_mu;
+  static std::map<int, int> cs_cache;
+  bool cached = false;
+  {
+    std::lock_guard<std::mutex> g(cs_mu);
+    auto it = cs_cache.find(n_cta);
+    if (it != cs_cache.end()) {
+      cs = it->second;
+      grid = (n_cta + cs - 1) / cs * cs;
+      cached = true;
+    }
+  }
+  for (int c = cached ? 0 : cs_max; c >= 2; c >>= 1) {
     const int g = (n_cta + c - 1) / c * c;
     cudaLaunchConfig_t q = {};
     q.gridDim = dim3(g);
@@ -650,6 +673,10 @@ extern "C" int b200_rdb_chain(const b200_chain_desc* d, const void* x0, const vo
       break;
     }
     (void)cudaGetLastError();
+  }
+  if (!cached) {
+    std::lock_guard<std::mutex> g(cs_mu);
+    cs_cache[n_cta] = cs;
   }
   p.cluster_size = cs;
   ::b200::launch_kernel(chain_epoch_bump_kernel, 1, 1, 0, as_stream(stream), epoch_dev);
