@@ -41,27 +41,30 @@ namespace b200 {
 namespace {
 
 constexpr int kThreads = 352;          // weights producer, 2 MMA issuers, 2 x 4 epilogue warps
-constexpr int kTileM = 128;
+constexpr int kTileM = 256;            // positions per CTA: two adjacent 128-row MMA halves sharing one operand region
 constexpr int kNTotal = 192;
-constexpr int kBStages = 3;
+constexpr int kBStages = 5;            // at most; p.b_stages slots are used (what fits beside the operand regions)
 constexpr uint32_t kBStageBytes = 24 * 1024;   // one 64-channel tap tile (24 KB) or 2-3 32-channel tap tiles (<= 24 KB)
 constexpr int kLLRowBytes = 256;       // 128 B of data (64 channels) in LL form
-constexpr int kMaxHalo = 131;          // w <= 128
+constexpr int kMaxHalo = 128;          // w <= 125
 
 struct ChainParams {
   CUtensorMap x_map;       // input of the first block: flat [P rows][>= 64 ch], box (64, box_rows)
-  CUtensorMap w_map[5];    // stage weights: 2-D [n_blocks * 9 * N_j rows][K_j], box (K_j, N_j)
+  CUtensorMap w_map[5][2]; // stage weights [n_blocks*9 taps][N_j rows][K_j] as 3-D maps; [j][0]: box = all rows (split = 0) or the
+                           // rows of the conv stage j completes; [j][1]: the remaining rows (split = 1 only)
   const b200_chain_stage* table;   // [n_blocks][5]
   int n_blocks;
   int x_ch;                // channel offset of the first block's input slice
   int Wp, HpWp, h, w, halo, nbox, box_rows;
   uint32_t a_bytes, a_region_bytes;
-  int range_pos0[2], range_len[2], range_tiles[2];   // the two position ranges (halves of the image group)
+  int pos0, range_len, n_tiles;   // first position, positions and 256-position super-tiles of the image group
+  int b_stages;            // weight ring slots in use
+  int mcast;               // multicast the stage weights to the cluster (one L2 read per cluster instead of per CTA)
+  int split;               // issue every stage as (completing columns, later convs) -- see part_rows()
   int tap_sign;            // +1 forward taps, -1 input-gradient taps
-  uint8_t* ll;             // LL exchange buffers [range][tile][side][parity][halo rows][256 B]
-  uint32_t ll_tile_stride; // bytes per (range, tile)
+  uint8_t* ll;             // LL exchange buffers [tile][side][parity][halo rows][256 B]
+  uint32_t ll_tile_stride; // bytes per tile
   const uint32_t* epoch;   // launch sequence number (bumped by a 1-thread kernel before this one)
-  int skew_cycles;         // tile 1 starts this many cycles after tile 0 (de-phases the two pipelines)
   int cluster_size;        // CTAs per thread-block cluster (1: every halo goes through L2)
   long long* dbg;
 };
@@ -183,53 +186,93 @@ __device__ __forceinline__ void dsmem_push(uint32_t dst_cluster, uint32_t src_ct
                "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
                : "memory");
 }
+// arrive on an mbarrier of a peer CTA (shared::cluster address)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+// TMA tile load delivered to the same shared-memory offset (and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_3d_mcast(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                  uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-__device__ __forceinline__ int taps_per_slot(int j) { return j == 0 ? 1 : (j == 1 ? 2 : 3); }
+// A stage may be issued in two parts: part 0 = the 32 (j = 4: 64) accumulator columns that stage j COMPLETES, part 1 =
+// the columns of the later convs, so that the epilogue / halo exchange of the completed columns overlaps part 1 on the
+// tensor pipe (the N = 32 MMAs of part 0 are shared-memory-operand bound: the price of starting the turnaround early).
+// split == 0: one part with all N = 192 - 32 j columns.
+__host__ __device__ __forceinline__ int part_rows(int j, int part, int split) {
+  if (!split) return part == 0 ? kNTotal - 32 * j : 0;
+  return part == 0 ? (j == 4 ? 64 : 32) : (j == 4 ? 0 : kNTotal - 32 * (j + 1));
+}
+__host__ __device__ __forceinline__ int part_tpb(int rows, int j) {   // taps per 24 KB weight slot
+  const int t = (int)kBStageBytes / (rows * (j == 0 ? 128 : 64));
+  return t > 9 ? 9 : t;
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 rdb_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // slice_ready[tile][parity]: operand region (tile, parity) complete = 4 epilogue warps (own rows, cluster-edge
-  // halos) + 1 expect_tx arrival covering the bytes the in-cluster neighbours push through DSMEM
-  __shared__ uint64_t b_full[kBStages], b_empty[kBStages], init_full[2], slice_ready[2][2], acc_ready[2];
+  // slice_ready[parity]: operand region `parity` complete = 8 epilogue warps (own rows, cluster-edge halos) + 1
+  // expect_tx arrival covering the bytes the in-cluster neighbours push through distributed shared memory
+  __shared__ uint64_t b_full[kBStages], b_empty[kBStages], grp_empty[kBStages], init_full, slice_ready[2], acc_ready;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int cta = blockIdx.x;
   const int crank = p.cluster_size > 1 ? (int)cluster_ctarank() : 0;
-  // tile `t` of this CTA = tile number `cta` of position range t; inactive when the range has fewer tiles
-  const bool active0 = cta < p.range_tiles[0], active1 = cta < p.range_tiles[1];
-  const int n_active = (active0 ? 1 : 0) + (active1 ? 1 : 0);
+  const bool active = cta < p.n_tiles;   // CTAs that only pad the grid to a multiple of the cluster size do nothing
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kBStages; ++s) {
+    // weight multicast: the active CTAs of a cluster (always a prefix of its ranks) consume identical weight tiles;
+    // the cluster's first CTA loads each tile ONCE from L2 and multicasts it, after every CTA reported the slot free
+    int grp_n = 1;
+    if (p.mcast) {
+      const int first = cta - crank;
+      grp_n = p.n_tiles - first < p.cluster_size ? p.n_tiles - first : p.cluster_size;
+      if (grp_n < 1) grp_n = 1;
+    }
+    for (int s = 0; s < p.b_stages; ++s) {
       mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], n_active > 0 ? n_active : 1);
+      mbar_init(&grp_empty[s], grp_n);
+      mbar_init(&b_empty[s], 2);       // both MMA issuers
     }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&init_full[t], 1);
-      mbar_init(&slice_ready[t][0], 5);
-      mbar_init(&slice_ready[t][1], 5);
-      mbar_init(&acc_ready[t], 1);
-    }
+    mbar_init(&init_full, 1);
+    mbar_init(&slice_ready[0], 9);
+    mbar_init(&slice_ready[1], 9);
+    mbar_init(&acc_ready, 2);
     mbar_fence_init();
   }
   if (warp == 1) {
     tmem_alloc(&tmem_base_s, 512);
     tmem_relinquish();
   }
-  // halo rows of the second (never TMA-loaded) operand region of each tile start as zeros: at the ends of a
-  // position range nobody ever writes them (the neighbouring positions are border rows of other images)
-  for (int i = threadIdx.x; i < 2 * 2 * p.halo * 8; i += kThreads) {
-    const int t = i / (2 * p.halo * 8), k = i % (2 * p.halo * 8);
-    const int row = k >> 3, ch = k & 7;
+  // halo rows of the second (never TMA-loaded) operand region start as zeros: at the ends of the position range nobody
+  // ever writes them (the neighbouring positions are border rows of other images)
+  for (int i = threadIdx.x; i < 2 * p.halo * 8; i += kThreads) {
+    const int row = i >> 3, ch = i & 7;
     const uint32_t R = row < p.halo ? (uint32_t)row : (uint32_t)(kTileM + row);
-    *reinterpret_cast<uint4*>(smem + (size_t)(t * 2 + 1) * p.a_region_bytes + (size_t)R * 128 + ch * 16) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(smem + (size_t)p.a_region_bytes + (size_t)R * 128 + ch * 16) = make_uint4(0, 0, 0, 0);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -237,147 +280,170 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
   tc_fence_after();
   if (p.cluster_size > 1) cluster_sync_all();   // every CTA's barriers are initialised before any peer pushes into it
   const uint32_t tmem = tmem_base_s;
-  const uint32_t b_ring_off = 4 * p.a_region_bytes;
+  const uint32_t b_ring_off = 2 * p.a_region_bytes;
   const int n_stages_total = p.n_blocks * 5;
   if (warp == 0) CDBG(0);
 
   if (warp == 0) {
-    // ------------------------------------------------------------ producer: initial operand regions, then weights
-    if (elect_one()) {
-      tma_prefetch_desc(&p.x_map);
-      for (int j = 0; j < 5; ++j) tma_prefetch_desc(&p.w_map[j]);
-      for (int t = 0; t < 2; ++t) {
-        if (!(t == 0 ? active0 : active1)) continue;
-        const int row0 = p.range_pos0[t] + cta * kTileM - p.halo;
-        uint8_t* sa = smem + (size_t)(t * 2) * p.a_region_bytes;
-        mbar_expect_tx(&init_full[t], p.a_bytes);
+    // ------------------------------------------------------------ producer: initial operand region, then weights
+    if (active) {
+      if (elect_one()) {
+        tma_prefetch_desc(&p.x_map);
+        for (int j = 0; j < 5; ++j) {
+          tma_prefetch_desc(&p.w_map[j][0]);
+          if (p.split && j < 4) tma_prefetch_desc(&p.w_map[j][1]);
+        }
+        const int row0 = p.pos0 + cta * kTileM - p.halo;
+        mbar_expect_tx(&init_full, p.a_bytes);
         for (int bx = 0; bx < p.nbox; ++bx)
-          tma_load_2d(sa + (size_t)bx * p.box_rows * 128, &p.x_map, &init_full[t], p.x_ch, row0 + bx * p.box_rows);
+          tma_load_2d(smem + (size_t)bx * p.box_rows * 128, &p.x_map, &init_full, p.x_ch, row0 + bx * p.box_rows);
       }
-    }
-    __syncwarp();
-    if (n_active > 0) {
+      __syncwarp();
       int bs = 0;
       uint32_t bph = 0;
+      uint16_t mcast_mask = 0;
+      if (p.mcast) {
+        const int first = cta - crank;
+        const int grp = p.n_tiles - first < p.cluster_size ? p.n_tiles - first : p.cluster_size;
+        mcast_mask = (uint16_t)((1u << grp) - 1u);
+      }
       for (int blk = 0; blk < p.n_blocks; ++blk) {
         for (int j = 0; j < 5; ++j) {
-          const int N = kNTotal - 32 * j;
-          const int tpb = taps_per_slot(j);
-          const uint32_t tap_bytes = (uint32_t)N * (j == 0 ? 128 : 64);
-          const int row_base = blk * 9 * N;
-          for (int t0 = 0; t0 < 9; t0 += tpb) {
-            const int nt = (9 - t0) < tpb ? (9 - t0) : tpb;
-            mbar_wait(&b_empty[bs], bph ^ 1);
-            if (elect_one()) {
-              mbar_expect_tx(&b_full[bs], tap_bytes * nt);
-              for (int q = 0; q < nt; ++q)
-                tma_load_2d(smem + b_ring_off + (size_t)bs * kBStageBytes + (size_t)q * tap_bytes, &p.w_map[j],
-                            &b_full[bs], 0, row_base + (t0 + q) * N);
-            }
-            __syncwarp();
-            if (++bs == kBStages) {
-              bs = 0;
-              bph ^= 1;
+          for (int part = 0; part < 2; ++part) {
+            const int rows = part_rows(j, part, p.split);
+            if (rows == 0) continue;
+            const int tpb = part_tpb(rows, j);
+            const uint32_t tap_bytes = (uint32_t)rows * (j == 0 ? 128 : 64);
+            const int row0 = part == 0 ? 0 : part_rows(j, 0, p.split);
+            for (int t0 = 0; t0 < 9; t0 += tpb) {
+              const int nt = (9 - t0) < tpb ? (9 - t0) : tpb;
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              if (elect_one()) {
+                mbar_expect_tx(&b_full[bs], tap_bytes * nt);
+                if (!p.mcast) {
+                  for (int q = 0; q < nt; ++q)
+                    tma_load_3d(smem + b_ring_off + (size_t)bs * kBStageBytes + (size_t)q * tap_bytes, &p.w_map[j][part],
+                                &b_full[bs], 0, row0, blk * 9 + t0 + q);
+                } else {
+                  // slot free here and its barrier armed -> tell the cluster's first CTA; it loads once for everybody
+                  mbar_arrive_cluster(mapa_cluster(smem_u32(&grp_empty[bs]), 0u));
+                  if (crank == 0) {
+                    mbar_wait_cluster(&grp_empty[bs], bph);
+                    for (int q = 0; q < nt; ++q)
+                      tma_load_3d_mcast(smem + b_ring_off + (size_t)bs * kBStageBytes + (size_t)q * tap_bytes,
+                                        &p.w_map[j][part], &b_full[bs], 0, row0, blk * 9 + t0 + q, mcast_mask);
+                  }
+                }
+              }
+              __syncwarp();
+              if (++bs == p.b_stages) {
+                bs = 0;
+                bph ^= 1;
+              }
             }
           }
         }
       }
     }
   } else if (warp == 1 || warp == 2) {
-    // ------------------------------------------------------------ MMA issuer of tile (warp - 1)
-    const int tile = warp - 1;
-    const bool active = tile == 0 ? active0 : active1;
+    // ------------------------------------------------------------ MMA issuer of half (warp - 1): rows [128 half, +128)
+    const int half = warp - 1;
     if (active) {
       const uint64_t desc_hi = make_smem_desc(0, 16, 1024, LAYOUT_SW128, 0);
       const uint64_t desc_b64 = make_smem_desc(0, 16, 512, LAYOUT_SW64, 0);   // 32-channel weight tiles: 64-byte rows
       const uint32_t smem_base = smem_u32(smem);
-      const uint32_t d_tile = tmem + tile * kNTotal;
+      const uint32_t d_half = tmem + half * kNTotal;
       uint32_t sh16[9];
 #pragma unroll
       for (int t = 0; t < 9; ++t) sh16[t] = (uint32_t)((p.tap_sign * ((t / 3 - 1) * p.Wp + (t % 3 - 1))) * 8);   // 128-B rows in 16-B units
-      if (tile == 1 && p.skew_cycles > 0) {
-        const long long t_go = clock64() + p.skew_cycles;
-        while (clock64() < t_go) {
-        }
-      }
       int bs = 0;
       uint32_t bph = 0;
       for (int s = 0; s < n_stages_total; ++s) {
         const int j = s % 5;
-        const int N = kNTotal - 32 * j;
-        const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
-        const uint32_t d_tmem = d_tile + 32 * j;
         if (s == 0) {
-          mbar_wait(&init_full[tile], 0);
+          mbar_wait(&init_full, 0);
         } else {
-          mbar_wait(&slice_ready[tile][s & 1], (uint32_t)(((s - 1) >> 1) & 1));
+          mbar_wait(&slice_ready[s & 1], (uint32_t)(((s - 1) >> 1) & 1));
         }
         tc_fence_after();
-        if (s < 7 && tile == 0) CDBG(2 + 8 * s);   // operand slice ready
-        const int tpb = taps_per_slot(j);
-        const uint32_t tap16 = ((uint32_t)N * (j == 0 ? 128 : 64)) >> 4;
-        const uint32_t a16 = (smem_base + (uint32_t)(tile * 2 + (s & 1)) * p.a_region_bytes + (uint32_t)p.halo * 128) >> 4;
-        for (int t0 = 0; t0 < 9; t0 += tpb) {
-          const int nt = (9 - t0) < tpb ? (9 - t0) : tpb;
-          mbar_wait(&b_full[bs], bph);
-          tc_fence_after();
-          const uint32_t b16 = (smem_base + b_ring_off + bs * kBStageBytes) >> 4;
-          if (elect_one()) {
-            if (j == 0) {
-              const uint32_t at = a16 + sh16[t0];
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(d_tmem, desc_hi | (uint64_t)((at + 2 * k) & 0x3FFF), desc_hi | (uint64_t)((b16 + 2 * k) & 0x3FFF), idesc,
-                         (t0 | k) != 0);
-            } else {
+        if (s < 7 && half == 0) CDBG(2 + 8 * s);   // operand slice ready
+        const uint32_t a16 = (smem_base + (uint32_t)(s & 1) * p.a_region_bytes + (uint32_t)(p.halo + half * 128) * 128) >> 4;
+        const int nk = (j == 0) ? 4 : 2;
+        const uint64_t bdesc_hi = (j == 0) ? desc_hi : desc_b64;
+        for (int part = 0; part < 2; ++part) {
+          const int rows = part_rows(j, part, p.split);
+          if (rows == 0) continue;
+          const uint32_t idesc = make_idesc_bf16(128, rows, 0, 0);
+          const uint32_t d_tmem = d_half + 32 * j + (part ? part_rows(j, 0, p.split) : 0);
+          const int tpb = part_tpb(rows, j);
+          const uint32_t tap16 = ((uint32_t)rows * (j == 0 ? 128 : 64)) >> 4;
+          for (int t0 = 0; t0 < 9; t0 += tpb) {
+            const int nt = (9 - t0) < tpb ? (9 - t0) : tpb;
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            const uint32_t b16 = (smem_base + b_ring_off + bs * kBStageBytes) >> 4;
+            if (elect_one()) {
               for (int q = 0; q < nt; ++q) {
                 const uint32_t at = a16 + sh16[t0 + q], bt = b16 + q * tap16;
+                // the first tap of a block's first stage zero-initialises the accumulator columns of its part
+                if (nk == 4) {
 #pragma unroll
-                for (int k = 0; k < 2; ++k)
-                  umma_f16(d_tmem, desc_hi | (uint64_t)((at + 2 * k) & 0x3FFF), desc_b64 | (uint64_t)((bt + 2 * k) & 0x3FFF), idesc,
-                           1u);
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16(d_tmem, desc_hi | (uint64_t)((at + 2 * k) & 0x3FFF), bdesc_hi | (uint64_t)((bt + 2 * k) & 0x3FFF), idesc,
+                             ((t0 + q) | k) != 0);
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 2; ++k)
+                    umma_f16(d_tmem, desc_hi | (uint64_t)((at + 2 * k) & 0x3FFF), bdesc_hi | (uint64_t)((bt + 2 * k) & 0x3FFF), idesc, 1u);
+                }
               }
+              umma_commit(&b_empty[bs]);
+              if (part == 0 && t0 + tpb >= 9) umma_commit(&acc_ready);   // the completing columns of this half are done
             }
-            umma_commit(&b_empty[bs]);
-            if (t0 + tpb >= 9) umma_commit(&acc_ready[tile]);
-          }
-          __syncwarp();
-          if (++bs == kBStages) {
-            bs = 0;
-            bph ^= 1;
+            __syncwarp();
+            if (++bs == p.b_stages) {
+              bs = 0;
+              bph ^= 1;
+            }
           }
         }
-        if (s < 7 && tile == 0) CDBG(3 + 8 * s);   // stage MMAs issued
+        if (s < 7 && half == 0) CDBG(3 + 8 * s);   // stage MMAs issued
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps: 3..6 -> tile 0, 7..10 -> tile 1
-    const int tile = (warp - 3) >> 2;
-    const bool active = tile == 0 ? active0 : active1;
+    // ------------------------------------------------------------ epilogue warps 3..10: one 256-row super-tile
     if (active) {
-      const int quad = warp & 3;
-      const int r = quad * 32 + lane;                       // row of the tile == TMEM lane
-      const int et = ((warp - 3) & 3) * 32 + lane;          // 0..127: index among the tile's epilogue threads
+      const int ew = warp - 3;                              // 0..7
+      const int quad = warp & 3;                            // TMEM lane quadrant this warp may read
+      const int half = ew >> 2;                             // warps 3..6 -> rows [0,128), 7..10 -> rows [128,256)
+      const int r = half * 128 + quad * 32 + lane;          // row of the super-tile
+      const int et = ew * 32 + lane;                        // 0..255: index among the epilogue threads
       const int lpos = cta * kTileM + r;                    // position within the range
-      const long long m = (long long)p.range_pos0[tile] + lpos;
+      const long long m = (long long)p.pos0 + lpos;
       const int rem = (int)(m % p.HpWp);
       const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
-      const bool valid = lpos < p.range_len[tile] && yp >= 1 && yp <= p.h && xp >= 1 && xp <= p.w;
-      const bool has_up = cta > 0, has_dn = cta + 1 < p.range_tiles[tile];
+      const bool valid = lpos < p.range_len && yp >= 1 && yp <= p.h && xp >= 1 && xp <= p.w;
+      const bool has_up = cta > 0, has_dn = cta + 1 < p.n_tiles;
       // neighbours inside the cluster are reached through distributed shared memory, the others through L2 (LL)
       const bool ds_up = has_up && crank > 0, ds_dn = has_dn && crank + 1 < p.cluster_size;
       const bool ll_up = has_up && !ds_up, ll_dn = has_dn && !ds_dn;
-      const uint32_t t_row = tmem + ((uint32_t)(quad * 32) << 16) + tile * kNTotal;
-      const uint32_t region0 = smem_u32(smem) + (uint32_t)(tile * 2) * p.a_region_bytes;
+      const uint32_t t_row = tmem + ((uint32_t)(quad * 32) << 16) + half * kNTotal;
+      const uint32_t region0 = smem_u32(smem);
       const uint32_t own_row = (uint32_t)(p.halo + r);
       const uint32_t own_xor = own_row & 7;
-      uint8_t* ll_me = p.ll + ((size_t)tile * p.range_tiles[0] + cta) * p.ll_tile_stride;
-      uint8_t* ll_upb = ll_me - p.ll_tile_stride;   // receive buffers of tile - 1 / tile + 1 of the same range
+      uint8_t* ll_me = p.ll + (size_t)cta * p.ll_tile_stride;
+      uint8_t* ll_upb = ll_me - p.ll_tile_stride;   // receive buffers of the super-tiles above / below
       uint8_t* ll_dnb = ll_me + p.ll_tile_stride;
       const uint32_t side_bytes = (uint32_t)p.halo * kLLRowBytes;   // one (side, parity) buffer
       const uint32_t flag0 = (*p.epoch) << 12;
       const uint32_t push_bytes = (uint32_t)p.halo * 128;
       const uint32_t ds_in_bytes = ((ds_up ? 1u : 0u) + (ds_dn ? 1u : 0u)) * push_bytes;
+      // rows [0, halo) (needed by the super-tile above) and [256 - halo, 256) (below) and the warps that own them
+      const bool in_top = r < p.halo, in_bot = r >= kTileM - p.halo;
+      const bool top_member = half == 0 && quad * 32 < p.halo;
+      const bool bot_member = half == 1 && (quad + 1) * 32 > 128 - p.halo;
+      const int top_count = (p.halo + 31) / 32 < 4 ? (p.halo + 31) / 32 : 4;
+      const int bot_count = 4 - ((128 - p.halo) > 0 ? (128 - p.halo) / 32 : 0);
       uint32_t acc_ph = 0;
       for (int s = 0; s < n_stages_total; ++s) {
         const int j = s % 5;
@@ -389,23 +455,16 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
         const uint32_t region = region0 + (uint32_t)pn * p.a_region_bytes;
         const uint32_t own_addr = region + own_row * 128;
         if (more && et == 0) {
-          // this phase of slice_ready[tile][pn] also waits for the bytes the in-cluster neighbours push
-          if (ds_in_bytes) mbar_expect_tx(&slice_ready[tile][pn], ds_in_bytes);
-          else mbar_arrive(&slice_ready[tile][pn]);
+          // this phase of slice_ready[pn] also waits for the bytes the in-cluster neighbours push
+          if (ds_in_bytes) mbar_expect_tx(&slice_ready[pn], ds_in_bytes);
+          else mbar_arrive(&slice_ready[pn]);
         }
         EpiPre q;
-        if (valid) {
-          prefetch32(e, q, 0, m);
-          if (j == 4) {   // second 32-channel half of the 64-channel stage: warm L1 now, the loads are issued after the first half
-            if (e.res1) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const __nv_bfloat16*>(e.res1) + m * e.res1_c + e.res1_coff + 32));
-            if (e.res2) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const __nv_bfloat16*>(e.res2) + m * e.res2_c + e.res2_coff + 32));
-            if (e.mask) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const __nv_bfloat16*>(e.mask) + m * e.mask_c + e.mask_coff + 32));
-          }
-        }
-        mbar_wait(&acc_ready[tile], acc_ph);
+        if (valid) prefetch32(e, q, 0, m);
+        mbar_wait(&acc_ready, acc_ph);
         acc_ph ^= 1;
         tc_fence_after();
-        if (s < 7 && warp == 3) CDBG(4 + 8 * s);   // stage MMAs complete
+        if (s < 7 && warp == 3) CDBG(4 + 8 * s);   // stage MMAs (completing columns) done
         __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(e.out);
         for (int c0 = 0; c0 < nch * 8; c0 += 32) {
           uint32_t acc[32];
@@ -428,7 +487,7 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
             for (int g = 0; g < 4; ++g) st_shared_v4(own_addr + ((uint32_t)((cb + g) ^ own_xor) << 4), o[g]);
           }
           // (2) halo rows for neighbours in OTHER clusters through L2 (LL: data + flag in every 8 bytes)
-          if (more && ll_up && r < p.halo) {
+          if (more && ll_up && in_top) {
             uint8_t* dst = ll_upb + (1 * 2 + par) * side_bytes + (size_t)r * kLLRowBytes + cb * 32;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -436,7 +495,7 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
               st_global_v4(dst + g * 32 + 16, o[g].z, flag, o[g].w, flag);
             }
           }
-          if (more && ll_dn && r >= kTileM - p.halo) {
+          if (more && ll_dn && in_bot) {
             uint8_t* dst = ll_dnb + (0 * 2 + par) * side_bytes + (size_t)(r - (kTileM - p.halo)) * kLLRowBytes + cb * 32;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -456,36 +515,37 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
         if (s < 7 && warp == 3) CDBG(6 + 8 * s);   // epilogue math + stores issued
         if (more) {
           fence_proxy_async();   // own rows (generic proxy) -> visible to the bulk-copy engine and the tensor core
-          // (4) push the halo rows to the in-cluster neighbours: ONE bulk copy per side, straight from this CTA's
-          //     operand region into the peer's (same 128B-swizzle phase: the row offset between the two is 128),
-          //     completing on the peer's slice_ready barrier
-          if (ds_up || ds_dn) {
-            named_bar_sync(1 + tile, 128);
-            if (et == 0) {
-              if (ds_up) {   // my rows [0, halo) -> bottom halo of the tile above
-                const uint32_t dst = mapa_cluster(region + (uint32_t)(p.halo + kTileM) * 128, (uint32_t)(crank - 1));
-                const uint32_t bar = mapa_cluster(smem_u32(&slice_ready[tile][pn]), (uint32_t)(crank - 1));
-                dsmem_push(dst, region + (uint32_t)p.halo * 128, push_bytes, bar);
-              }
-              if (ds_dn) {   // my rows [128 - halo, 128) -> top halo of the tile below
-                const uint32_t dst = mapa_cluster(region, (uint32_t)(crank + 1));
-                const uint32_t bar = mapa_cluster(smem_u32(&slice_ready[tile][pn]), (uint32_t)(crank + 1));
-                dsmem_push(dst, region + (uint32_t)kTileM * 128, push_bytes, bar);
-              }
+          // (4) push the halo rows to the in-cluster neighbours: ONE bulk copy per side, straight from this CTA's operand
+          //     region into the peer's (same 128B-swizzle phase: the row offset between the two is 256), completing on
+          //     the peer's slice_ready barrier.  Only the warps that own those rows synchronise.
+          if (ds_up && top_member) {
+            named_bar_sync(1, 32 * top_count);
+            if (quad == 0 && lane == 0) {   // my rows [0, halo) -> bottom halo of the super-tile above
+              const uint32_t dst = mapa_cluster(region + (uint32_t)(p.halo + kTileM) * 128, (uint32_t)(crank - 1));
+              const uint32_t bar = mapa_cluster(smem_u32(&slice_ready[pn]), (uint32_t)(crank - 1));
+              dsmem_push(dst, region + (uint32_t)p.halo * 128, push_bytes, bar);
+            }
+          }
+          if (ds_dn && bot_member) {
+            named_bar_sync(2, 32 * bot_count);
+            if (quad == 3 && lane == 0) {   // my rows [256 - halo, 256) -> top halo of the super-tile below
+              const uint32_t dst = mapa_cluster(region, (uint32_t)(crank + 1));
+              const uint32_t bar = mapa_cluster(smem_u32(&slice_ready[pn]), (uint32_t)(crank + 1));
+              dsmem_push(dst, region + (uint32_t)kTileM * 128, push_bytes, bar);
             }
           }
           // (5) halo rows from neighbours in other clusters: poll the LL buffers (all of a thread's polls in flight
           //     together; items whose flags have not landed are polled again after a short sleep)
           if (ll_up || ll_dn) {
             const int per_side = p.halo * nch;
-            constexpr int kBatch = 5;
-            for (int base = et; base < 2 * per_side; base += 128 * kBatch) {
+            constexpr int kBatch = 3;
+            for (int base = et; base < 2 * per_side; base += 256 * kBatch) {
               const uint8_t* src[kBatch];
               uint32_t dst[kBatch];
               unsigned pending = 0;
 #pragma unroll
               for (int qi = 0; qi < kBatch; ++qi) {
-                const int i = base + qi * 128;
+                const int i = base + qi * 256;
                 src[qi] = nullptr;
                 dst[qi] = 0;
                 if (i < 2 * per_side) {
@@ -520,7 +580,7 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
             fence_proxy_async();
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(&slice_ready[tile][pn]);
+          if (lane == 0) mbar_arrive(&slice_ready[pn]);
         }
         if (s < 7 && warp == 3) CDBG(5 + 8 * s);   // slice turned around (this warp's part)
       }
@@ -547,13 +607,17 @@ using namespace b200;
 
 extern "C" int b200_rdb_chain_geometry(int32_t n, int32_t h, int32_t w, int32_t* n_cta, int64_t* ll_bytes) {
   const int Hp = h + 2, Wp = w + 2;
-  const int n0 = (n + 1) / 2;
-  const long long len0 = (long long)n0 * Hp * Wp;
-  const int tiles = (int)((len0 + kTileM - 1) / kTileM);
+  const long long len = (long long)n * Hp * Wp;
+  const int tiles = (int)((len + kTileM - 1) / kTileM);
   if (n_cta) *n_cta = tiles;
   const int halo = Wp + 1;
-  if (ll_bytes) *ll_bytes = (int64_t)2 * tiles * 4 * halo * kLLRowBytes;
-  return 0;
+  if (ll_bytes) *ll_bytes = (int64_t)tiles * 4 * halo * kLLRowBytes;
+  // the shared-memory budget: two operand regions + at least three 24 KB weight slots
+  const int region = kTileM + 2 * halo;
+  const int nbox = (region + 255) / 256;
+  const int box_rows = (((region + nbox - 1) / nbox) + 7) & ~7;
+  const int a_region = (nbox * box_rows * 128 + 1023) & ~1023;
+  return (halo <= kMaxHalo && 2 * a_region + 3 * (int)kBStageBytes + 1024 <= 227 * 1024) ? 0 : 1;
 }
 
 // One launch = a chain of n_blocks dense blocks (forward, or gather-form input gradient when flip_taps) over
@@ -576,22 +640,22 @@ extern "C" int b200_rdb_chain(const b200_chain_desc* d, const void* x0, const vo
   p.box_rows = (((region + p.nbox - 1) / p.nbox) + 7) & ~7;
   p.a_bytes = (uint32_t)p.nbox * p.box_rows * 128;
   p.a_region_bytes = (p.a_bytes + 1023) & ~1023u;
-  const int kSmemBytes = (int)(4 * p.a_region_bytes + kBStages * kBStageBytes + 1024);
-  B200_REQUIRE(kSmemBytes <= 227 * 1024, "b200_rdb_chain: image too wide for the shared-memory operand regions (w=%d)", d->w);
+  int b_stages = (227 * 1024 - 1024 - 2 * (int)p.a_region_bytes) / (int)kBStageBytes;
+  if (b_stages > kBStages) b_stages = kBStages;
+  B200_REQUIRE(b_stages >= 3, "b200_rdb_chain: image too wide for the shared-memory operand regions (w=%d)", d->w);
+  p.b_stages = b_stages;
+  const int kSmemBytes = (int)(2 * p.a_region_bytes + b_stages * kBStageBytes + 1024);
   B200_ENSURE_SMEM(rdb_chain_kernel, kSmemBytes);
-  const int n0 = (d->n + 1) / 2, n1 = d->n - n0;
   const long long P_total = (long long)d->n_total * p.HpWp;
-  p.range_pos0[0] = d->img0 * p.HpWp;
-  p.range_len[0] = n0 * p.HpWp;
-  p.range_pos0[1] = (d->img0 + n0) * p.HpWp;
-  p.range_len[1] = n1 * p.HpWp;
-  for (int t = 0; t < 2; ++t) p.range_tiles[t] = (p.range_len[t] + kTileM - 1) / kTileM;
-  const int n_cta = p.range_tiles[0];
+  p.pos0 = d->img0 * p.HpWp;
+  p.range_len = d->n * p.HpWp;
+  p.n_tiles = (p.range_len + kTileM - 1) / kTileM;
+  const int n_cta = p.n_tiles;
   const int sms = sm_count();
-  B200_REQUIRE(n_cta <= sms, "b200_rdb_chain: %d tile pairs exceed the %d SMs (split the batch)", n_cta, sms);
+  B200_REQUIRE(n_cta <= sms, "b200_rdb_chain: %d super-tiles exceed the %d SMs (split the batch)", n_cta, sms);
   int n_cta_chk;
   int64_t need;
-  b200_rdb_chain_geometry(d->n, d->h, d->w, &n_cta_chk, &need);
+  B200_REQUIRE(b200_rdb_chain_geometry(d->n, d->h, d->w, &n_cta_chk, &need) == 0, "b200_rdb_chain: unsupported geometry");
   B200_REQUIRE(ll_bytes >= need, "b200_rdb_chain: exchange buffer of %lld bytes needed", (long long)need);
   p.ll = reinterpret_cast<uint8_t*>(ll_buf);
   p.ll_tile_stride = (uint32_t)(4 * p.halo * kLLRowBytes);
@@ -601,12 +665,12 @@ extern "C" int b200_rdb_chain(const b200_chain_desc* d, const void* x0, const vo
   p.x_ch = d->x_coff;
   p.tap_sign = d->flip_taps ? -1 : 1;
   {
-    static int skew = -1;
-    if (skew < 0) {
-      const char* e = getenv("B200_CHAIN_SKEW");
-      skew = e ? atoi(e) : 1500;
+    static int split = -1;
+    if (split < 0) {
+      const char* e = getenv("B200_CHAIN_SPLIT");
+      split = e ? atoi(e) : 1;   // measured on B200, config 2: 4.82 + 5.21 ms (fwd + bwd trunk) vs 5.12 + 5.38 ms unsplit
     }
-    p.skew_cycles = skew;
+    p.split = split ? 1 : 0;
   }
   {
     const char* e = getenv("B200_CHAIN_DBG_PTR");
@@ -622,12 +686,16 @@ extern "C" int b200_rdb_chain(const b200_chain_desc* d, const void* x0, const vo
     B200_REQUIRE(w_stage[j], "b200_rdb_chain: null stage weights");
     const int N = kNTotal - 32 * j;
     const uint64_t kc = (j == 0) ? 64 : 32;
-    uint64_t dims[2] = {kc, (uint64_t)d->n_blocks * 9 * N};
-    uint64_t strides[1] = {kc * 2};
-    uint32_t box[2] = {(uint32_t)kc, (uint32_t)N};
-    if (make_tensor_map(&p.w_map[j], w_stage[j], 2, dims, strides, box, nullptr,
-                        kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))
-      return 1;
+    for (int part = 0; part < 2; ++part) {
+      const int rows = part_rows(j, part, p.split);
+      if (rows == 0) continue;
+      uint64_t dims[3] = {kc, (uint64_t)N, (uint64_t)d->n_blocks * 9};
+      uint64_t strides[2] = {kc * 2, (uint64_t)N * kc * 2};
+      uint32_t box[3] = {(uint32_t)kc, (uint32_t)rows, 1};
+      if (make_tensor_map(&p.w_map[j][part], w_stage[j], 3, dims, strides, box, nullptr,
+                          kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))
+        return 1;
+    }
   }
   // Thread-block clusters: neighbouring tiles inside a cluster exchange their halo rows through distributed
   // shared memory (bulk copy + remote mbarrier), only the cluster-edge halos go through L2.  The largest cluster
@@ -679,6 +747,14 @@ extern "C" int b200_rdb_chain(const b200_chain_desc* d, const void* x0, const vo
     cs_cache[n_cta] = cs;
   }
   p.cluster_size = cs;
+  {
+    static int mc = -1;
+    if (mc < 0) {
+      const char* e = getenv("B200_CHAIN_MCAST");
+      mc = e ? atoi(e) : 0;   // opt-in: measured SLOWER (4.93 vs 4.82 ms): one CTA issuing the cluster's loads + a per-slot handshake
+    }
+    p.mcast = (mc && cs > 1) ? 1 : 0;
+  }
   ::b200::launch_kernel(chain_epoch_bump_kernel, 1, 1, 0, as_stream(stream), epoch_dev);
   B200_LAUNCH_CHECK();
   cudaLaunchConfig_t cfg = {};

@@ -139,16 +139,19 @@ class RRDBNetEngine:
 
     @staticmethod
     def _chain_geometry(n, h, w):
+        """(CTAs, exchange-buffer bytes, supported) of one rdb_chain launch over n images"""
         n_cta, ll = CT.c_int32(0), CT.c_int64(0)
-        lib.b200_rdb_chain_geometry(n, h, w, CT.byref(n_cta), CT.byref(ll))
-        return n_cta.value, ll.value
+        rc = lib.b200_rdb_chain_geometry(n, h, w, CT.byref(n_cta), CT.byref(ll))
+        return n_cta.value, ll.value, rc == 0
 
     def _chain_groups(self, N, h, w):
-        """image groups of one rdb_chain launch: two position ranges (halves of the group) of <= #SM 128-row tiles"""
-        half = (sm_count_hint() * 128) // ((h + 2) * (w + 2))
-        if half < 1:
+        """image groups of one rdb_chain launch: as many images as give <= #SM 256-position super-tiles (one per CTA,
+        all co-resident); None when the geometry is not supported (image too wide for the shared-memory regions)"""
+        if not self._chain_geometry(1, h, w)[2]:
             return None
-        g = 2 * half
+        g = (sm_count_hint() * 256) // ((h + 2) * (w + 2))
+        if g < 1:
+            return None
         return [(i, min(g, N - i)) for i in range(0, N, g)]
 
     # ------------------------------------------------------------------ plans
@@ -192,7 +195,7 @@ class RRDBNetEngine:
         f.add(lib.b200_pad_copy, P(ctx.B[0]), Bc[0], 0, P(ctx.F0), nf, 0, N, h, w, nf)
         groups = self._image_groups(N, h, w) if self.persist else []
         ctx.flags = torch.zeros(256, dtype=torch.int32, device=dev) if self.persist else None
-        use_chain = self.chain and w + 3 <= 131
+        use_chain = self.chain
         ctx.chain_groups = self._chain_groups(N, h, w) if use_chain else None
         use_chain = ctx.chain_groups is not None
         if use_chain:
