@@ -59,6 +59,7 @@ struct ChainParams {
   uint32_t a_bytes, a_region_bytes;
   int pos0, range_len, n_tiles;   // first position, positions and 256-position super-tiles of the image group
   int b_stages;            // weight ring slots in use
+  int n_regions;           // operand regions in rotation (2, or 3 with split stages)
   int mcast;               // multicast the stage weights to the cluster (one L2 read per cluster instead of per CTA)
   int split;               // issue every stage as (completing columns, later convs) -- see part_rows()
   int tap_sign;            // +1 forward taps, -1 input-gradient taps
@@ -235,7 +236,7 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // slice_ready[parity]: operand region `parity` complete = 8 epilogue warps (own rows, cluster-edge halos) + 1
   // expect_tx arrival covering the bytes the in-cluster neighbours push through distributed shared memory
-  __shared__ uint64_t b_full[kBStages], b_empty[kBStages], grp_empty[kBStages], init_full, slice_ready[2], acc_ready;
+  __shared__ uint64_t b_full[kBStages], b_empty[kBStages], grp_empty[kBStages], init_full, slice_ready[3], acc_ready;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -258,8 +259,7 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
       mbar_init(&b_empty[s], 2);       // both MMA issuers
     }
     mbar_init(&init_full, 1);
-    mbar_init(&slice_ready[0], 9);
-    mbar_init(&slice_ready[1], 9);
+    for (int i = 0; i < 3; ++i) mbar_init(&slice_ready[i], 9);
     mbar_init(&acc_ready, 2);
     mbar_fence_init();
   }
@@ -267,12 +267,17 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
     tmem_alloc(&tmem_base_s, 512);
     tmem_relinquish();
   }
-  // halo rows of the second (never TMA-loaded) operand region start as zeros: at the ends of the position range nobody
+  // Operand regions rotate: stage s reads region s % nreg, its epilogue (and the neighbours) fill region (s+1) % nreg.
+  // nreg = 2 suffices when a stage is issued in one piece; with split stages the later-conv MMAs of stage s-1 may still
+  // read region (s-1) % nreg while a neighbour already pushes its stage-s halo rows, so three regions rotate.
+  // halo rows of the never TMA-loaded regions start as zeros: at the ends of the position range nobody
   // ever writes them (the neighbouring positions are border rows of other images)
-  for (int i = threadIdx.x; i < 2 * p.halo * 8; i += kThreads) {
-    const int row = i >> 3, ch = i & 7;
+  const int nreg = p.n_regions;
+  for (int i = threadIdx.x; i < (nreg - 1) * 2 * p.halo * 8; i += kThreads) {
+    const int reg = 1 + i / (2 * p.halo * 8), k = i % (2 * p.halo * 8);
+    const int row = k >> 3, ch = k & 7;
     const uint32_t R = row < p.halo ? (uint32_t)row : (uint32_t)(kTileM + row);
-    *reinterpret_cast<uint4*>(smem + (size_t)p.a_region_bytes + (size_t)R * 128 + ch * 16) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(smem + (size_t)reg * p.a_region_bytes + (size_t)R * 128 + ch * 16) = make_uint4(0, 0, 0, 0);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -280,7 +285,7 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
   tc_fence_after();
   if (p.cluster_size > 1) cluster_sync_all();   // every CTA's barriers are initialised before any peer pushes into it
   const uint32_t tmem = tmem_base_s;
-  const uint32_t b_ring_off = 2 * p.a_region_bytes;
+  const uint32_t b_ring_off = (uint32_t)nreg * p.a_region_bytes;
   const int n_stages_total = p.n_blocks * 5;
   if (warp == 0) CDBG(0);
 
@@ -363,11 +368,11 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
         if (s == 0) {
           mbar_wait(&init_full, 0);
         } else {
-          mbar_wait(&slice_ready[s & 1], (uint32_t)(((s - 1) >> 1) & 1));
+          mbar_wait(&slice_ready[s % nreg], (uint32_t)(((s - 1) / nreg) & 1));
         }
         tc_fence_after();
         if (s < 7 && half == 0) CDBG(2 + 8 * s);   // operand slice ready
-        const uint32_t a16 = (smem_base + (uint32_t)(s & 1) * p.a_region_bytes + (uint32_t)(p.halo + half * 128) * 128) >> 4;
+        const uint32_t a16 = (smem_base + (uint32_t)(s % nreg) * p.a_region_bytes + (uint32_t)(p.halo + half * 128) * 128) >> 4;
         const int nk = (j == 0) ? 4 : 2;
         const uint64_t bdesc_hi = (j == 0) ? desc_hi : desc_b64;
         for (int part = 0; part < 2; ++part) {
@@ -450,7 +455,7 @@ rdb_chain_kernel(const __grid_constant__ ChainParams p) {
         const b200_chain_stage e = p.table[s];
         const int nch = (j == 4) ? 8 : 4;              // 16-byte chunks of the finished slice (64 or 32 channels)
         const uint32_t flag = flag0 + (uint32_t)s + 1u;
-        const int par = s & 1, pn = par ^ 1;           // the finished slice becomes operand region `pn`
+        const int par = s & 1, pn = (s + 1) % nreg;    // LL buffer parity; the finished slice becomes operand region `pn`
         const bool more = s + 1 < n_stages_total;
         const uint32_t region = region0 + (uint32_t)pn * p.a_region_bytes;
         const uint32_t own_addr = region + own_row * 128;
@@ -640,11 +645,25 @@ extern "C" int b200_rdb_chain(const b200_chain_desc* d, const void* x0, const vo
   p.box_rows = (((region + p.nbox - 1) / p.nbox) + 7) & ~7;
   p.a_bytes = (uint32_t)p.nbox * p.box_rows * 128;
   p.a_region_bytes = (p.a_bytes + 1023) & ~1023u;
-  int b_stages = (227 * 1024 - 1024 - 2 * (int)p.a_region_bytes) / (int)kBStageBytes;
+  {
+    static int split = -1;
+    if (split < 0) {
+      const char* e = getenv("B200_CHAIN_SPLIT");
+      split = e ? atoi(e) : 1;
+    }
+    p.split = split ? 1 : 0;
+  }
+  p.n_regions = p.split ? 3 : 2;
+  int b_stages = (227 * 1024 - 1024 - p.n_regions * (int)p.a_region_bytes) / (int)kBStageBytes;
+  if (b_stages < 3 && p.split) {   // not enough room for three regions: one-piece stages with two
+    p.split = 0;
+    p.n_regions = 2;
+    b_stages = (227 * 1024 - 1024 - 2 * (int)p.a_region_bytes) / (int)kBStageBytes;
+  }
   if (b_stages > kBStages) b_stages = kBStages;
   B200_REQUIRE(b_stages >= 3, "b200_rdb_chain: image too wide for the shared-memory operand regions (w=%d)", d->w);
   p.b_stages = b_stages;
-  const int kSmemBytes = (int)(2 * p.a_region_bytes + b_stages * kBStageBytes + 1024);
+  const int kSmemBytes = (int)(p.n_regions * p.a_region_bytes + b_stages * kBStageBytes + 1024);
   B200_ENSURE_SMEM(rdb_chain_kernel, kSmemBytes);
   const long long P_total = (long long)d->n_total * p.HpWp;
   p.pos0 = d->img0 * p.HpWp;
@@ -664,14 +683,6 @@ extern "C" int b200_rdb_chain(const b200_chain_desc* d, const void* x0, const vo
   p.n_blocks = d->n_blocks;
   p.x_ch = d->x_coff;
   p.tap_sign = d->flip_taps ? -1 : 1;
-  {
-    static int split = -1;
-    if (split < 0) {
-      const char* e = getenv("B200_CHAIN_SPLIT");
-      split = e ? atoi(e) : 1;   // measured on B200, config 2: 4.82 + 5.21 ms (fwd + bwd trunk) vs 5.12 + 5.38 ms unsplit
-    }
-    p.split = split ? 1 : 0;
-  }
   {
     const char* e = getenv("B200_CHAIN_DBG_PTR");
     p.dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
