@@ -497,3 +497,26 @@ def test_training_steps_are_bit_reproducible(tmp_path):
         for k, v in runs[0][which].items():
             assert torch.equal(v, runs[1][which][k]), "run-to-run difference in %s" % k
     assert any(not torch.equal(v, init[0][k]) for k, v in runs[0][1].items())
+
+
+@pytest.mark.parametrize("h,w", [(256, 256), (40, 200)])
+def test_rrdbnet_eval_on_large_images(h, w):
+    """SRModel.test() / the reference validation loop run G on whole images (sr_model.py:269-277): LR inputs far wider
+    than a training crop must work.  Such shapes are outside the chain kernel's shared-memory budget and take the
+    per-conv flat kernels, whose operand region shrinks its pipeline depth for wide rows."""
+    from oracle import esrgan_oracle as O
+    from trainner_b200 import networks
+    from trainner_b200.architectures import RRDBNet_arch
+    torch.manual_seed(2)
+    net = RRDBNet_arch.RRDBNet(3, 3, 64, 2).cuda()
+    networks.init_weights(net, "kaiming", 0.3)
+    net.eval()
+    x = torch.rand(1, 3, h, w, device="cuda")
+    with torch.no_grad():
+        y = net(x)
+        sd = OrderedDict((k, v.detach()) for k, v in net.state_dict().items())
+        y32 = O.rrdbnet_forward(sd, x, 2, "upconv")
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y16 = O.rrdbnet_forward(sd, x, 2, "upconv").float()
+    assert tuple(y.shape) == (1, 3, 4 * h, 4 * w)
+    assert rel(y, y32) <= max(1e-2, 1.25 * rel(y16, y32)), (rel(y, y32), rel(y16, y32))
