@@ -242,16 +242,17 @@ def run_reference_cudnn(args):
 
 
 def ncu_traffic_per_launch(tag):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
-    capture of one training step (profiles/r01_v5_conv_flat_dram_traffic.txt); None for other kernels."""
-    path = os.path.join(ROOT, "profiles", "r01_v5_conv_flat_dram_traffic.txt")
-    if tag != "conv_flat" or not os.path.exists(path):
-        return None, None
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from this round's committed
+    `ncu --set full --cache-control none` capture (profiles/r02_ncu_full_<kernel>.txt, written by
+    tools/summarize_ncu.py from tools/collect_ncu.sh's .ncu-rep); None when no capture of that kernel is committed."""
     import re
-    m = re.search(r"DRAM read ([0-9.]+) MB, DRAM write ([0-9.]+) MB", open(path).read())
-    if not m:
+    path = os.path.join(ROOT, "profiles", "r02_ncu_full_%s.txt" % tag)
+    if not os.path.exists(path):
         return None, None
-    return (float(m.group(1)) + float(m.group(2))) * 1e6, "profiles/r01_v5_conv_flat_dram_traffic.txt"
+    vals = [float(a) + float(b) for a, b in re.findall(r"DRAM read ([0-9.]+) MB write ([0-9.]+) MB", open(path).read())]
+    if not vals:
+        return None, None
+    return sum(vals) / len(vals) * 1e6, "profiles/r02_ncu_full_%s.txt (mean of %d captured launches)" % (tag, len(vals))
 
 
 def main():
@@ -354,15 +355,19 @@ def main():
         peak = pk["bf16_tflops_sustained"]
         traffic, traffic_src = ncu_traffic_per_launch(tag)
         roof = {"bound": "tensor", "kernel": tag, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, mean)",
+                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu --set full, warm caches)",
                 "traffic_source": traffic_src, "launches_per_step": cnt,
                 "avg_launch_ms": t_ms / cnt, "share_of_kernel_time": t_ms / total_ms if total_ms else None,
                 "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
                 "per_kernel": {k: {"launches": v[0], "ms": round(v[1], 3),
                                    "tflops": round(v[2] / (v[1] * 1e-3) / 1e12, 1) if v[1] > 0 and v[2] > 0 else None}
                                for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
+                # algorithmic FLOPs of the reference's step; the D-step re-uses the D(fake) / D(real) forwards
+                # of the G-step (value-identical), so 2 x 9.123 GMAC per image are not executed
                 "step_algorithmic_tflops": GFLOP_PER_IMAGE_STEP * 1e-3 * args.batch,
-                "step_frac_of_peak": (GFLOP_PER_IMAGE_STEP * 1e9 * (args.batch / (ms / 1e3))) / (peak * 1e12)}
+                "step_frac_of_peak": (GFLOP_PER_IMAGE_STEP * 1e9 * (args.batch / (ms / 1e3))) / (peak * 1e12),
+                "step_executed_tflops": (GFLOP_PER_IMAGE_STEP - 2 * 2 * 9.123) * 1e-3 * args.batch,
+                "step_frac_of_peak_executed": ((GFLOP_PER_IMAGE_STEP - 2 * 2 * 9.123) * 1e9 * (args.batch / (ms / 1e3))) / (peak * 1e12)}
         if not args.no_cpu_baseline and world == 1 and rank == 0:
             c_ips, c_dt, threads = cpu_reference_steps(args, 6, 1)
             cpu_base = {"value": c_ips * px, "unit": "HR-px/s", "images_per_sec": c_ips, "cores": threads,

@@ -32,6 +32,7 @@ struct WgradParams {
   uint32_t stage_bytes;
   float scale;
   float* dw;
+  int pack2;   // cin <= 64: the two 64-channel atoms of the M = 128 operand hold TWO TAPS of the same 64 input channels
   float* ws;   // split-K partials [split][tap][co][ci] (nullptr when splits == 1: single owner, direct +=)
 };
 
@@ -87,7 +88,8 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       int t, mb, nb, ks;
       decode(item, t, mb, nb, ks);
-      const int ky = t / p.kw, kx = t % p.kw;
+      const int ta = p.pack2 ? 2 * t : t;   // first (or only) tap of the item
+      const int ky = ta / p.kw, kx = ta % p.kw;
       const int pt0 = ks * p.tiles_per_split;
       const int pt1 = min(pt0 + p.tiles_per_split, p.pixel_tiles);
       for (int pt = pt0; pt < pt1; ++pt) {
@@ -101,8 +103,13 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
           mbar_expect_tx(&full_bar[stage], (2 + p.n_atoms) * kAtomBytes);
           const int cx = x0 * p.stride + kx - p.pad, cy = y0 * p.stride + ky - p.pad;
           tma_load_4d(sx, &p.x_map, &full_bar[stage], p.x_coff + mb * 128, cx, cy, n0);
-          tma_load_4d(sx + kAtomBytes, &p.x_map, &full_bar[stage], p.x_coff + mb * 128 + 64, cx, cy,
-                      n0);
+          if (p.pack2) {   // atom 1 = the same 64 channels seen through the item's second tap
+            const int t2 = (2 * t + 1 < p.taps) ? 2 * t + 1 : 2 * t;
+            const int cx2 = x0 * p.stride + (t2 % p.kw) - p.pad, cy2 = y0 * p.stride + (t2 / p.kw) - p.pad;
+            tma_load_4d(sx + kAtomBytes, &p.x_map, &full_bar[stage], p.x_coff, cx2, cy2, n0);
+          } else {
+            tma_load_4d(sx + kAtomBytes, &p.x_map, &full_bar[stage], p.x_coff + mb * 128 + 64, cx, cy, n0);
+          }
           for (int j = 0; j < p.n_atoms; ++j)
             tma_load_4d(sy + j * kAtomBytes, &p.dy_map, &full_bar[stage],
                         p.dy_coff + nb * p.BN + j * 64, x0, y0, n0);
@@ -163,7 +170,12 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       int t, mb, nb, ks;
       decode(item, t, mb, nb, ks);
-      const int ci = mb * 128 + m;
+      int ci = mb * 128 + m;
+      if (p.pack2) {   // rows 0..63 -> tap 2t, rows 64..127 -> tap 2t + 1 (absent for the last item of an odd tap count)
+        ci = m & 63;
+        t = 2 * t + (m >> 6);
+        if (t >= p.taps) ci = p.cin;   // nothing to store
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem + ((uint32_t)(quad * 32) << 16) + acc * acc_cols;
@@ -212,21 +224,28 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 }
 
 // Second pass of the split-K weight gradient: dW (OIHW) += scale * sum over the pixel splits, in split order.
-// ws is tap-major [split][tap][co][ci] (the layout the tcgen05 epilogue writes with full 128-byte lines).
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw,
+// ws is tap-major [split][tap][co][ci] (the layout the tcgen05 epilogue writes with full 128-byte lines); one block owns
+// (co, 128 input channels): it reads each tap's 128 values coalesced, transposes through shared memory and updates
+// the 128 * taps CONTIGUOUS floats of dW[co][ci0 .. ci0+128][taps] with coalesced read-modify-writes.
+__global__ void __launch_bounds__(128) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw,
                                                            int splits, int taps, int cout, int cin, float scale) {
   pdl_trigger();
   pdl_wait();
-  const long long per = (long long)taps * cout * cin;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int ci = (int)(i % cin);
-    const long long r = i / cin;
-    const int co = (int)(r % cout), t = (int)(r / cout);
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += ws[(long long)k * per + i];
-    dw[((size_t)co * cin + ci) * taps + t] += scale * s;
+  __shared__ float tile[128 * 17];   // [ci][tap], taps <= 16, padded
+  const int co = blockIdx.y, ci0 = blockIdx.x * 128, tid = threadIdx.x;
+  const int nci = cin - ci0 < 128 ? cin - ci0 : 128;
+  const size_t per = (size_t)taps * cout * cin;
+  if (tid < nci) {
+    for (int t = 0; t < taps; ++t) {
+      const float* src = ws + ((size_t)t * cout + co) * cin + ci0 + tid;
+      float s = 0.f;
+      for (int k = 0; k < splits; ++k) s += src[(size_t)k * per];
+      tile[tid * 17 + t] = s;
+    }
   }
+  __syncthreads();
+  float* dst = dw + ((size_t)co * cin + ci0) * taps;
+  for (int i = tid; i < nci * taps; i += 128) dst[i] += scale * tile[(i / taps) * 17 + (i % taps)];
 }
 
 // One thread converts all taps of one (row, col) weight: the fp32 source is read as `taps` consecutive
@@ -336,12 +355,14 @@ extern "C" int b200_conv_wgrad(const b200_wgrad_desc* d, const void* x, const vo
   p.cout = d->cout;
   p.x_coff = d->x_coff;
   p.dy_coff = d->dy_coff;
+  p.pack2 = (d->cin <= 64) ? 1 : 0;
   p.m_blocks = (d->cin + 127) / 128;
   int BN = d->cout <= 128 ? ((d->cout + 15) / 16) * 16 : 128;
   p.BN = BN;
   p.n_atoms = (BN + 63) / 64;
   p.n_blocks = (d->cout + BN - 1) / BN;
-  const int base_items = p.taps * p.m_blocks * p.n_blocks;
+  const int tap_items = p.pack2 ? (p.taps + 1) / 2 : p.taps;
+  const int base_items = tap_items * p.m_blocks * p.n_blocks;
   const int sms = sm_count();
   int splits = (2 * sms + base_items - 1) / base_items;  // ~2 items per SM
   if (splits > p.pixel_tiles) splits = p.pixel_tiles;
@@ -384,10 +405,9 @@ extern "C" int b200_conv_wgrad(const b200_wgrad_desc* d, const void* x, const vo
   ::b200::launch_kernel(conv_wgrad_kernel, grid, kThreads, smem, as_stream(stream), p);
   B200_LAUNCH_CHECK();
   if (p.ws) {
-    const long long per = (long long)p.taps * d->cout * d->cin;
-    long long blocks = (per + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    ::b200::launch_kernel(wgrad_reduce_kernel, (int)blocks, 256, 0, as_stream(stream), (const float*)p.ws, dw, p.splits,
+    B200_REQUIRE(p.taps <= 16, "b200_conv_wgrad: at most 16 taps");
+    dim3 rgrid((d->cin + 127) / 128, d->cout);
+    ::b200::launch_kernel(wgrad_reduce_kernel, rgrid, 128, 0, as_stream(stream), (const float*)p.ws, dw, p.splits,
                           p.taps, (int)d->cout, (int)d->cin, d->scale);
     B200_LAUNCH_CHECK();
   }

@@ -613,7 +613,9 @@ using namespace b200;
 extern "C" int b200_rdb_chain_geometry(int32_t n, int32_t h, int32_t w, int32_t* n_cta, int64_t* ll_bytes) {
   const int Hp = h + 2, Wp = w + 2;
   const long long len = (long long)n * Hp * Wp;
-  const int tiles = (int)((len + kTileM - 1) / kTileM);
+  // the last (w + 3) positions of the range are border positions of the last image: a super-tile holding only those has
+  // nothing to compute (8 images of 66 x 66: 136 tiles = 34 clusters of 4 instead of 137)
+  const int tiles = (int)((len - (Wp + 1) + kTileM - 1) / kTileM);
   if (n_cta) *n_cta = tiles;
   const int halo = Wp + 1;
   if (ll_bytes) *ll_bytes = (int64_t)tiles * 4 * halo * kLLRowBytes;
@@ -668,7 +670,7 @@ extern "C" int b200_rdb_chain(const b200_chain_desc* d, const void* x0, const vo
   const long long P_total = (long long)d->n_total * p.HpWp;
   p.pos0 = d->img0 * p.HpWp;
   p.range_len = d->n * p.HpWp;
-  p.n_tiles = (p.range_len + kTileM - 1) / kTileM;
+  p.n_tiles = (p.range_len - p.halo + kTileM - 1) / kTileM;   // see b200_rdb_chain_geometry
   const int n_cta = p.n_tiles;
   const int sms = sm_count();
   B200_REQUIRE(n_cta <= sms, "b200_rdb_chain: %d super-tiles exceed the %d SMs (split the batch)", n_cta, sms);
