@@ -225,27 +225,29 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 
 // Second pass of the split-K weight gradient: dW (OIHW) += scale * sum over the pixel splits, in split order.
 // ws is tap-major [split][tap][co][ci] (the layout the tcgen05 epilogue writes with full 128-byte lines); one block owns
-// (co, 128 input channels): it reads each tap's 128 values coalesced, transposes through shared memory and updates
-// the 128 * taps CONTIGUOUS floats of dW[co][ci0 .. ci0+128][taps] with coalesced read-modify-writes.
-__global__ void __launch_bounds__(128) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw,
+// (co, 32 input channels): 32 x 8 threads read the taps' values coalesced along ci, transpose through shared memory and
+// update the 32 * taps CONTIGUOUS floats of dW[co][ci0 .. ci0+32][taps] with coalesced read-modify-writes.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw,
                                                            int splits, int taps, int cout, int cin, float scale) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float tile[128 * 17];   // [ci][tap], taps <= 16, padded
-  const int co = blockIdx.y, ci0 = blockIdx.x * 128, tid = threadIdx.x;
-  const int nci = cin - ci0 < 128 ? cin - ci0 : 128;
+  __shared__ float tile[32 * 17];   // [ci][tap], taps <= 16, padded
+  const int co = blockIdx.y, ci0 = blockIdx.x * 32, tid = threadIdx.x;
+  const int cl = tid & 31, tl = tid >> 5;   // 32 input channels x 8 tap lanes
+  const int nci = cin - ci0 < 32 ? cin - ci0 : 32;
   const size_t per = (size_t)taps * cout * cin;
-  if (tid < nci) {
-    for (int t = 0; t < taps; ++t) {
-      const float* src = ws + ((size_t)t * cout + co) * cin + ci0 + tid;
+  if (cl < nci) {
+    for (int t = tl; t < taps; t += 8) {
+      const float* src = ws + ((size_t)t * cout + co) * cin + ci0 + cl;
       float s = 0.f;
+#pragma unroll 4
       for (int k = 0; k < splits; ++k) s += src[(size_t)k * per];
-      tile[tid * 17 + t] = s;
+      tile[cl * 17 + t] = s;
     }
   }
   __syncthreads();
   float* dst = dw + ((size_t)co * cin + ci0) * taps;
-  for (int i = tid; i < nci * taps; i += 128) dst[i] += scale * tile[(i / taps) * 17 + (i % taps)];
+  for (int i = tid; i < nci * taps; i += 256) dst[i] += scale * tile[(i / taps) * 17 + (i % taps)];
 }
 
 // One thread converts all taps of one (row, col) weight: the fp32 source is read as `taps` consecutive
@@ -406,8 +408,8 @@ extern "C" int b200_conv_wgrad(const b200_wgrad_desc* d, const void* x, const vo
   B200_LAUNCH_CHECK();
   if (p.ws) {
     B200_REQUIRE(p.taps <= 16, "b200_conv_wgrad: at most 16 taps");
-    dim3 rgrid((d->cin + 127) / 128, d->cout);
-    ::b200::launch_kernel(wgrad_reduce_kernel, rgrid, 128, 0, as_stream(stream), (const float*)p.ws, dw, p.splits,
+    dim3 rgrid((d->cin + 31) / 32, d->cout);
+    ::b200::launch_kernel(wgrad_reduce_kernel, rgrid, 256, 0, as_stream(stream), (const float*)p.ws, dw, p.splits,
                           p.taps, (int)d->cout, (int)d->cin, d->scale);
     B200_LAUNCH_CHECK();
   }
