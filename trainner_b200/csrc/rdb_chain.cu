@@ -1,31 +1,35 @@
-// Whole-trunk residual-dense-block chain in ONE persistent launch (sm_100a, tcgen05 + TMEM + TMA).
+// Whole-trunk residual-dense-block chain in ONE persistent launch (sm_100a: tcgen05 + TMEM + TMA + clusters/DSMEM).
 //
-// A dense block is 5 stacked 3x3 convs where conv_k consumes [x, x1 .. x_{k-1}].  Computed conv by conv,
-// four of them have only 32 output channels and tcgen05.mma is shared-memory-operand bound at 40 % of the
-// tensor pipe (N = 32; profiles/r01_umma_pipe_probe.log).  Here a block is computed INPUT SLICE by input slice:
-//   stage j consumes the newest slice S_j (x for j = 0, then x1..x4) and adds its contribution to ALL convs
-//   that still need it:  D[:, 32j:192] += S_j (*) W_stage_j      (N = 192 - 32 j, K = 64 or 32 per tap)
-// and the fp32 partial sums of a 128-position tile (192 columns) stay in TMEM for the whole block.  After stage j
-// the 32 (last stage: 64) columns that just became complete are finished (bias / LeakyReLU or mask / residuals),
-// written to HBM (saved activation / gradient) and -- as bf16, already in the 128B-swizzled K-major layout --
-// straight back into the CTA's own shared-memory operand region: they ARE the next stage's A operand.
-// The output of stage 4 is the x slice of the NEXT block, so the whole trunk (69 blocks x 5 stages) runs in
-// one launch with the activations never leaving the SM except as stores.
+// A dense block is 5 stacked 3x3 convs where conv_k consumes [x, x1 .. x_{k-1}].  Computed conv by conv, four of them
+// have only 32 output channels and tcgen05.mma is shared-memory-operand bound at 40 % of the tensor pipe (N = 32;
+// profiles/r01_umma_pipe_probe.log).  Here a block is computed INPUT SLICE by input slice:
+//   stage j consumes the newest slice S_j (x for j = 0, then x1..x4) and adds its contribution to ALL convs that still
+//   need it:  D[:, 32j:192] += S_j (*) W_stage_j      (N = 192 - 32 j, K = 64 or 32 per tap)
+// and the fp32 partial sums of a CTA's 256-position super-tile (two 128-row halves x 192 columns) stay in TMEM for
+// the whole block.  After stage j the 32 (last stage: 64) columns that just became complete are finished (bias /
+// LeakyReLU or mask / residuals), written to HBM (saved activation / gradient) and -- as bf16, already in the
+// 128B-swizzled K-major layout -- straight back into the CTA's own shared-memory operand region: they ARE the next
+// stage's A operand.  The output of stage 4 is the x slice of the NEXT block, so the whole trunk (69 blocks x 5
+// stages) runs in one launch with the activations never leaving the SM except as stores.
 //
-// Each CTA owns TWO 128-position tiles of the flat (zero-bordered) position space, one from each half of the
-// image group (so the two tiles never depend on each other), with one MMA-issuing warp and four epilogue
-// warps per tile; the stage weights stream once per CTA through a TMA ring shared by both tiles.  While one
-// tile's finished slice is being turned around (TMEM -> registers -> smem, ~1 k cycles) the other tile's MMAs
-// keep the tensor pipe busy.
+// One CTA per super-tile of the flat (zero-bordered) position space, all co-resident; warp roles: TMA weight producer,
+// two MMA issuers (one per 128-row half, sharing every weight tile), eight epilogue warps.  The stage weights stream
+// through a TMA ring.  A stage is issued in two parts -- first the columns it completes, then the columns of the later
+// convs -- so that the turnaround of the finished slice (TMEM -> registers -> smem, halo exchange) overlaps the second
+// part on the tensor pipe.  The operand regions rotate (stage s reads region s % 3, fills region (s+1) % 3) so that a
+// neighbour's halo rows can never land in rows the tensor core still reads.
 //
-// Halo rows (the +-(w+3) positions a 3x3 tap reaches beyond the tile) belong to the neighbouring tiles = the
-// neighbouring CTAs.  They travel through L2 in "LL" form: every 16-byte store carries 8 bytes of data and two
-// copies of a 4-byte sequence flag (8-byte atomicity), the receiver polls the data itself -- no fence, no
-// separate flag round trip (the round-1 kernel rdb_persist.cu spent ~6.5 k cycles per stage on store -> fence
-// -> flag -> acquire -> TMA reload of the whole operand).  All CTAs are co-resident (cooperative launch).
+// Halo rows (the +-(w+3) positions a 3x3 tap reaches beyond the super-tile) belong to the neighbouring CTAs:
+//   * inside a thread-block cluster they travel through DISTRIBUTED SHARED MEMORY: one cp.async.bulk
+//     shared::cta -> shared::cluster copy per side, straight from this CTA's operand region into the peer's (same
+//     swizzle phase: the row offset is 256), completing on the peer's mbarrier;
+//   * across cluster edges through L2 in "LL" form: every 16-byte store carries 8 bytes of data and two copies of a
+//     4-byte sequence flag (8-byte atomicity), the receiver polls the data itself -- no fence, no separate flag
+//     (the round-1 kernel rdb_persist.cu spent ~6.5 k cycles per stage on store -> fence -> flag -> acquire -> TMA).
 //
 // The gather-form input gradient of a block has exactly the same shape with the slices taken in reverse
 // (dO, dY4 .. dY1 -> d(x4) .. d(x)), so the backward trunk is the same kernel with flipped taps.
+// Measured history and the in-kernel timeline: DESIGN.md section 4, tools/time_chain.py.
 //
 // Reference: ResidualDenseBlock_5C.forward + RRDB residuals (RRDBNet_arch.py:89-96,150-163), the ShortcutBlock
 // trunk (block.py:184-192) and their autograd input gradients.
