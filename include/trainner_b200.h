@@ -58,6 +58,10 @@ typedef struct {
   int32_t accumulate;
   int32_t mask_c, mask_coff, mask_lo, mask_hi;  /* mask tensor [n, h_buf, w_buf, mask_c]     */
   float mask_slope;
+  /* 4: ONE launch computes the four output-parity classes of the dgrad of a 4x4 stride-2 conv: class c uses taps
+   * [c*ntaps, (c+1)*ntaps) of the tap tables and writes at out_off + (c >> 1, c & 1) (out_mul must be (2,2)).
+   * 0 / 1: a single conv. */
+  int32_t parity_classes;
 } b200_conv_desc;
 
 int b200_conv_igemm(const b200_conv_desc* d, const void* x, const void* w_packed, const float* bias,

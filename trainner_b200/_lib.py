@@ -32,6 +32,7 @@ class ConvDesc(C.Structure):
         ("accumulate", C.c_int32),
         ("mask_c", C.c_int32), ("mask_coff", C.c_int32), ("mask_lo", C.c_int32), ("mask_hi", C.c_int32),
         ("mask_slope", C.c_float),
+        ("parity_classes", C.c_int32),
     ]
 
 

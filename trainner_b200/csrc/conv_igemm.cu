@@ -32,6 +32,7 @@ struct IgemmParams {
   CUtensorMap w_map;
   int tw, th, tn;
   int tiles_x, tiles_y, tiles_n, n_blocks, total_tiles;
+  int cls_tiles;   // tiles per output-parity class (== total_tiles when the launch is a single conv)
   int Nimg, Ho, Wo;
   int aux_h, aux_w, aux_my, aux_oy, aux_mx, aux_ox;  // grid of the residual / mask tensors
   int in_stride, in_off_y, in_off_x;
@@ -66,10 +67,13 @@ struct IgemmParams {
 
 struct TileCoord {
   int nb, x0, y0, n0;
+  int cls;   // output-parity class of a merged launch: taps [cls * ntaps, +ntaps), output offset + (cls >> 1, cls & 1)
 };
 
 __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
   TileCoord t;
+  t.cls = tile / p.cls_tiles;
+  tile -= t.cls * p.cls_tiles;
   t.nb = tile % p.n_blocks;
   int r = tile / p.n_blocks;
   t.x0 = (r % p.tiles_x) * p.tw;
@@ -205,7 +209,8 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
-      for (int t = 0; t < p.ntaps; ++t) {
+      for (int t0 = 0; t0 < p.ntaps; ++t0) {
+        const int t = tc.cls * p.ntaps + t0;
         const int cx = tc.x0 * p.in_stride + p.in_off_x + p.tap_dx[t];
         const int cy = tc.y0 * p.in_stride + p.in_off_y + p.tap_dy[t];
         const int wt = p.tap_w[t];
@@ -279,11 +284,12 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
       const bool valid = (x < p.Wo) && (y < p.Ho) && (n < p.Nimg);
       // residual / mask tensors live on the output buffer's grid at the placed coordinates
       // (or on the logical grid when the store replicates 2x2)
-      const long long pix_lin = ((long long)n * p.aux_h + (y * p.aux_my + p.aux_oy)) * p.aux_w +
-                                (x * p.aux_mx + p.aux_ox);
+      const int cy_ = tc.cls >> 1, cx_ = tc.cls & 1;   // parity offsets of a merged launch (0 otherwise)
+      const long long pix_lin = ((long long)n * p.aux_h + (y * p.aux_my + p.aux_oy + cy_)) * p.aux_w +
+                                (x * p.aux_mx + p.aux_ox + cx_);
       __nv_bfloat16* out_px = p.out + (long long)n * p.o_sn +
-                              (long long)(y * p.o_my + p.o_oy) * p.o_sy +
-                              (long long)(x * p.o_mx + p.o_ox) * p.o_sx;
+                              (long long)(y * p.o_my + p.o_oy + cy_) * p.o_sy +
+                              (long long)(x * p.o_mx + p.o_ox + cx_) * p.o_sx;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem + ((uint32_t)(quad * 32) << 16) + acc * p.acc_cols;
@@ -450,7 +456,8 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
-      for (int t = 0; t < p.ntaps; ++t) {
+      for (int t0 = 0; t0 < p.ntaps; ++t0) {
+        const int t = tc.cls * p.ntaps + t0;
         const int cx = tc.x0 * p.in_stride + p.in_off_x + p.tap_dx[t];
         const int cy = tc.y0 * p.in_stride + p.in_off_y + p.tap_dy[t];
         const int wt = p.tap_w[t];
@@ -526,11 +533,12 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
       const TileCoord tc = decode_tile(p, tile);
       const int x = tc.x0 + ix, y = tc.y0 + iy, n = tc.n0 + in_;
       const bool valid = (x < p.Wo) && (y < p.Ho) && (n < p.Nimg);
-      const long long pix_lin = ((long long)n * p.aux_h + (y * p.aux_my + p.aux_oy)) * p.aux_w +
-                                (x * p.aux_mx + p.aux_ox);
+      const int cy_ = tc.cls >> 1, cx_ = tc.cls & 1;   // parity offsets of a merged launch (0 otherwise)
+      const long long pix_lin = ((long long)n * p.aux_h + (y * p.aux_my + p.aux_oy + cy_)) * p.aux_w +
+                                (x * p.aux_mx + p.aux_ox + cx_);
       __nv_bfloat16* out_px = p.out + (long long)n * p.o_sn +
-                              (long long)(y * p.o_my + p.o_oy) * p.o_sy +
-                              (long long)(x * p.o_mx + p.o_ox) * p.o_sx;
+                              (long long)(y * p.o_my + p.o_oy + cy_) * p.o_sy +
+                              (long long)(x * p.o_mx + p.o_ox + cx_) * p.o_sx;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem + ((uint32_t)(quad * 32) << 16) + acc * 2 * p.acc_cols + half * p.acc_cols;
@@ -618,19 +626,21 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
   int bn256 = BN;
   while (bn256 >= 128 && bn256 % 32 == 0 && d->cout % (bn256 / 2) == 0 && pixel_tiles * nblocks(bn256) < sms)
     bn256 /= 2;
-  const bool use256 = pixel_tiles * nblocks(bn256) >= (sms * 3) / 4;
+  const int ncls = d->parity_classes == 4 ? 4 : 1;
+  const bool use256 = pixel_tiles * nblocks(bn256) * ncls >= (sms * 3) / 4;
   if (use256) {
     BN = bn256;
   } else {
     pixel_tiles = geometry(128);
-    while (BN >= 128 && BN % 32 == 0 && d->cout % (BN / 2) == 0 && pixel_tiles * nblocks(BN) < sms) BN /= 2;
+    while (BN >= 128 && BN % 32 == 0 && d->cout % (BN / 2) == 0 && pixel_tiles * nblocks(BN) * ncls < sms) BN /= 2;
   }
   p.BN = BN;
   p.acc_cols = (BN + 31) & ~31;
   p.acc_stages = (4 * p.acc_cols <= 512) ? 2 : 1;
   p.a_bytes = use256 ? 2 * kABytes : kABytes;
   p.n_blocks = nblocks(BN);
-  p.total_tiles = pixel_tiles * p.n_blocks;
+  p.cls_tiles = pixel_tiles * p.n_blocks;
+  p.total_tiles = p.cls_tiles * ncls;
   p.Nimg = d->n;
   p.Ho = d->h_out;
   p.Wo = d->w_out;
@@ -641,7 +651,12 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
   p.k_chunks = (d->cin + 63) / 64;
   p.last_k16 = (d->cin % 64 == 0) ? 4 : (d->cin % 64) / 16;
   p.ntaps = d->ntaps;
-  for (int t = 0; t < d->ntaps; ++t) {
+  B200_REQUIRE(d->parity_classes == 0 || d->parity_classes == 1 || d->parity_classes == 4,
+               "b200_conv_igemm: parity_classes must be 0, 1 or 4");
+  B200_REQUIRE(d->ntaps * ncls <= B200_MAX_TAPS, "b200_conv_igemm: %d taps x %d classes exceed the tap table", d->ntaps, ncls);
+  B200_REQUIRE(ncls == 1 || (d->out_mul_y == 2 && d->out_mul_x == 2 && !d->upsample2x),
+               "b200_conv_igemm: parity classes need out_mul = (2, 2)");
+  for (int t = 0; t < d->ntaps * ncls; ++t) {
     p.tap_dy[t] = d->tap_dy[t];
     p.tap_dx[t] = d->tap_dx[t];
     p.tap_w[t] = d->tap_w[t];

@@ -149,12 +149,13 @@ class DiscriminatorEngine:
                 add_igemm(b, d, ctx.dZ[i], L.w_dgr, mask=mask_t, y=ctx.dA[i])
             else:
                 assert L.stride == 2 and L.kh == 4 and L.pad == 1
-                for py in (0, 1):
-                    for px in (0, 1):
-                        d = make_conv_desc(N, ho, ho, L.cout, 0, L.cout, hi // 2, hi // 2, hi, hi, L.cin, 0, L.cin,
-                                           taps_dgrad_s2_k4(py, px), L.taps, L.dgr_rows, L.dgr_cols,
-                                           out_mul=(2, 2), out_off=(py, px), **mask_kw)
-                        add_igemm(b, d, ctx.dZ[i], L.w_dgr, mask=mask_t, y=ctx.dA[i])
+                # the four output-parity classes (each a 2x2-tap conv at half resolution) in ONE launch: the
+                # small late layers are launch-bound, 4 launches of a few CTAs each wasted most of the GPU
+                taps4 = [t for py in (0, 1) for px in (0, 1) for t in taps_dgrad_s2_k4(py, px)]
+                d = make_conv_desc(N, ho, ho, L.cout, 0, L.cout, hi // 2, hi // 2, hi, hi, L.cin, 0, L.cin,
+                                   taps4, L.taps, L.dgr_rows, L.dgr_cols, out_mul=(2, 2), out_off=(0, 0),
+                                   parity_classes=4, **mask_kw)
+                add_igemm(b, d, ctx.dZ[i], L.w_dgr, mask=mask_t, y=ctx.dA[i])
         # conv0 (thin -> wide, LeakyReLU): dA[0] now holds the pre-activation gradient
         if wgrad:
             b.add(lib.b200_conv3x3_thin_wgrad, P(ctx.x), P(ctx.dA[0]), P(g(self.conv0.weight)),

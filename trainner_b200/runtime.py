@@ -336,11 +336,12 @@ def make_conv_desc(n, h_in, w_in, cx, cin_off, cin, h_out, w_out, h_buf, w_buf, 
                    taps, w_taps, w_rows, w_cols, in_stride=1, in_off=(0, 0), out_mul=(1, 1),
                    out_off=(0, 0), upsample=0, alpha=1.0, act=0, slope=0.0, beta1=0.0, beta2=0.0,
                    res_nch=0, res1_c=0, res1_coff=0, res2_c=0, res2_coff=0, accumulate=0, mask_c=0,
-                   mask_coff=0, mask_lo=0, mask_hi=0, mask_slope=0.0):
+                   mask_coff=0, mask_lo=0, mask_hi=0, mask_slope=0.0, parity_classes=0):
     d = ConvDesc()
     d.n, d.h_in, d.w_in, d.cx, d.cin_off, d.cin = n, h_in, w_in, cx, cin_off, cin
     d.h_out, d.w_out, d.h_buf, d.w_buf, d.cy, d.cout_off, d.cout = h_out, w_out, h_buf, w_buf, cy, cout_off, cout
-    d.ntaps = len(taps)
+    d.parity_classes = parity_classes
+    d.ntaps = len(taps) // (parity_classes or 1)   # `taps` lists the classes' taps one class after the other
     for i, (dy, dx, wi) in enumerate(taps):
         d.tap_dy[i], d.tap_dx[i], d.tap_w[i] = dy, dx, wi
     d.in_stride, d.in_off_y, d.in_off_x = in_stride, in_off[0], in_off[1]
@@ -357,10 +358,11 @@ def make_conv_desc(n, h_in, w_in, cx, cin_off, cin, h_out, w_out, h_buf, w_buf, 
 
 def add_igemm(plan, desc, x, w, bias=None, res1=None, res2=None, mask=None, y=None):
     plan.keep(desc)
-    flops = 2.0 * desc.n * desc.h_out * desc.w_out * desc.cout * desc.cin * desc.ntaps
-    info = "cin%d cout%d %dx%dx%d taps%d s%d%s%s" % (desc.cin, desc.cout, desc.n, desc.h_out, desc.w_out, desc.ntaps,
-                                                   desc.in_stride, " acc" if desc.accumulate else "",
-                                                   " up" if desc.upsample2x else "")
+    ncls = desc.parity_classes or 1
+    flops = 2.0 * desc.n * desc.h_out * desc.w_out * desc.cout * desc.cin * desc.ntaps * ncls
+    info = "cin%d cout%d %dx%dx%d taps%d s%d%s%s%s" % (desc.cin, desc.cout, desc.n, desc.h_out, desc.w_out, desc.ntaps,
+                                                     desc.in_stride, " acc" if desc.accumulate else "",
+                                                     " up" if desc.upsample2x else "", " x4cls" if ncls == 4 else "")
     plan.add(lib.b200_conv_igemm, C.byref(desc), P(x), P(w), P(bias), P(res1), P(res2), P(mask), P(y),
              flops=flops, tag="conv_igemm", info=info)
 
