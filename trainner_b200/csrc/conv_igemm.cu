@@ -621,19 +621,36 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
     return p.tiles_x * p.tiles_y * p.tiles_n;
   };
   auto nblocks = [&](int bn) { return (d->cout + bn - 1) / bn; };
-  int BN = d->cout <= 256 ? ((d->cout + 15) / 16) * 16 : 256;
-  int pixel_tiles = geometry(256);
-  int bn256 = BN;
-  while (bn256 >= 128 && bn256 % 32 == 0 && d->cout % (bn256 / 2) == 0 && pixel_tiles * nblocks(bn256) < sms)
-    bn256 /= 2;
+  // Tile shape (128 or 256 pixel rows x BN output channels) by a small cost model instead of "fill the SMs": many of
+  // these layers are L2 -> shared-memory bound, and narrow tiles re-fetch the activation tile once per output-channel
+  // block.  cost = max(tensor time of the slowest SM, operand bytes / L2 bandwidth), both in SM cycles; the model
+  // reproduces the measured times within ~15 % (512->512 @16x16, 256 x 64 tiles: 82 k cycles; @32x32, 256 x 256: 143 k).
   const int ncls = d->parity_classes == 4 ? 4 : 1;
-  const bool use256 = pixel_tiles * nblocks(bn256) * ncls >= (sms * 3) / 4;
-  if (use256) {
-    BN = bn256;
-  } else {
-    pixel_tiles = geometry(128);
-    while (BN >= 128 && BN % 32 == 0 && d->cout % (BN / 2) == 0 && pixel_tiles * nblocks(BN) * ncls < sms) BN /= 2;
+  const int bn0 = d->cout <= 256 ? ((d->cout + 15) / 16) * 16 : 256;
+  const long long k_iters_h = (long long)d->ntaps * ((d->cin + 63) / 64);
+  double best_cost = 1e30;
+  int best_rows = 128, BN = bn0;
+  for (int rows = 256; rows >= 128; rows -= 128) {
+    const int px_tiles = geometry(rows);
+    for (int bn = bn0;; bn /= 2) {
+      const long long tiles = (long long)px_tiles * nblocks(bn) * ncls;
+      const long long waves = (tiles + sms - 1) / sms;
+      const double mma_one = bn / 2.0 > (4096.0 + bn * 32.0) / 128.0 ? bn / 2.0 : (4096.0 + bn * 32.0) / 128.0;
+      const double t_mma = (double)waves * k_iters_h * 4.0 * (rows / 128) * mma_one;
+      const double t_l2 = (double)tiles * k_iters_h * (rows * 128.0 + bn * 128.0) / 4500.0;   // chip-wide L2 -> SM bytes/cycle
+      const double t_sm = (double)waves * k_iters_h * (rows * 128.0 + bn * 128.0) / 40.0;      // one SM's L2 ingest bytes/cycle
+      double cost = t_mma > t_l2 ? t_mma : t_l2;
+      cost = (cost > t_sm ? cost : t_sm) + 3000.0 * waves;
+      if (cost < best_cost) {
+        best_cost = cost;
+        best_rows = rows;
+        BN = bn;
+      }
+      if (!(bn >= 64 && bn % 32 == 0 && d->cout % (bn / 2) == 0)) break;
+    }
   }
+  const bool use256 = best_rows == 256;
+  int pixel_tiles = geometry(best_rows);
   p.BN = BN;
   p.acc_cols = (BN + 31) & ~31;
   p.acc_stages = (4 * p.acc_cols <= 512) ? 2 : 1;
