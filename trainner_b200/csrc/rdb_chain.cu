@@ -752,7 +752,13 @@ extern "C" int b200_rdb_chain(const b200_chain_desc* d, const void* x0, const vo
     q.attrs = qa;
     q.numAttrs = 1;
     int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, rdb_chain_kernel, &q) == cudaSuccess && max_clusters * c >= g) {
+    const cudaError_t qe = cudaOccupancyMaxActiveClusters(&max_clusters, rdb_chain_kernel, &q);
+    // measured on B200 with this kernel's 226 KB of shared memory: 74 clusters of 2, 33 clusters of 4 (config 2 needs
+    // 34: one short, so the default run uses pairs and half of the tile sides go through L2)
+    if (getenv("B200_CHAIN_DEBUG"))
+      fprintf(stderr, "rdb_chain: cluster size %d -> max active clusters %d (%s), need %d\n", c, max_clusters,
+              cudaGetErrorString(qe), g / c);
+    if (qe == cudaSuccess && max_clusters * c >= g) {
       cs = c;
       grid = g;
       break;
