@@ -716,11 +716,11 @@ extern "C" int b200_rdb_chain(const b200_chain_desc* d, const void* x0, const vo
   }
   // Thread-block clusters: neighbouring tiles inside a cluster exchange their halo rows through distributed
   // shared memory (bulk copy + remote mbarrier), only the cluster-edge halos go through L2.  The largest cluster
-  // size (<= B200_CHAIN_CLUSTER, default 4) whose clusters are all co-resident is used.
+  // size (<= B200_CHAIN_CLUSTER, default 8) whose clusters are all co-resident is used.
   static int cs_max = -1;
   if (cs_max < 0) {
     const char* e = getenv("B200_CHAIN_CLUSTER");
-    cs_max = e ? atoi(e) : 4;
+    cs_max = e ? atoi(e) : 8;
     if (cs_max < 1) cs_max = 1;
     if (cs_max > 8) cs_max = 8;
   }
@@ -738,7 +738,7 @@ extern "C" int b200_rdb_chain(const b200_chain_desc* d, const void* x0, const vo
       cached = true;
     }
   }
-  for (int c = cached ? 0 : cs_max; c >= 2; c >>= 1) {
+  for (int c = cached ? 0 : cs_max; c >= 2; --c) {   // any size, not only powers of two: 6 fits where 4 + 4 + .. does not
     const int g = (n_cta + c - 1) / c * c;
     cudaLaunchConfig_t q = {};
     q.gridDim = dim3(g);
