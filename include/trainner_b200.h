@@ -280,6 +280,11 @@ int b200_bn_stats(const void* z, float* stats, int64_t npix, int32_t c, b200_str
 int b200_bn_finalize(const float* stats, float* mean_invstd, float* running_mean,
                      float* running_var, int64_t npix, int32_t c, float momentum, float eps,
                      b200_stream_t stream);
+/* b200_bn_stats + b200_bn_finalize in one launch: the block that produces the totals also writes mean / invstd
+ * and updates the running statistics (the default training-mode forward; nn.BatchNorm2d semantics).          */
+int b200_bn_stats_finalize(const void* z, float* stats, float* mean_invstd, float* running_mean,
+                           float* running_var, int64_t npix, int32_t c, float momentum, float eps,
+                           b200_stream_t stream);
 int b200_bn_apply_lrelu(const void* z, const float* mean_invstd, const float* gamma,
                         const float* beta, void* a, int64_t npix, int32_t c, float slope,
                         b200_stream_t stream);

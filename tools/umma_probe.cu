@@ -117,7 +117,8 @@ probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             uint32_t a_addr = smem_u32(sA + c * a_chunk_bytes) + p.shift * 128 + k * 32;
             uint32_t b_addr = smem_u32(sB + c * b_chunk_bytes) + k * 32;
             uint32_t bo = p.base_off ? ((a_addr >> 7) & 7) : 0;
-            uint64_t ad = make_smem_desc(a_addr, 16, 1024, LAYOUT_SW128, bo);
+            // reps (unused in this mode) = rows between consecutive 8-row groups of A (0: the canonical 8)
+            uint64_t ad = make_smem_desc(a_addr, 16, p.reps ? p.reps * 128 : 1024, LAYOUT_SW128, bo);
             uint64_t bd = make_smem_desc(b_addr, 16, 1024, LAYOUT_SW128, 0);
             umma_f16(tmem, ad, bd, idesc, (c | k) != 0);
           }
@@ -158,8 +159,8 @@ probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     }
   } else {
     // rate probe: zero operands resident in smem, 4 rotating stage addresses.
-    const uint32_t a_stage = 144 * 128;      // 128 rows x 64 bf16 (+16 rows of slack for shifted starts)
-    const uint32_t b_stage = 256 * 128;      // 32 KB
+    const uint32_t a_stage = 176 * 128;      // 128 rows x 64 bf16 (+ slack for shifted starts / strided groups)
+    const uint32_t b_stage = 128 * 128;      // 16 KB (N <= 128 here)
     for (uint32_t i = threadIdx.x; i < (4 * (a_stage + b_stage)) / 16; i += blockDim.x)
       reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -172,7 +173,7 @@ probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
       const uint32_t a_kstep = p.a_mn ? 16 * 128 : 32;
       const uint64_t adesc_hi = p.a_mn ? (make_smem_desc(0, 8192, 1024, LAYOUT_SW128, 0))
-                                       : (make_smem_desc(0, 16, 1024, LAYOUT_SW128, 0));
+                                       : (make_smem_desc(0, 16, p.K ? p.K * 128 : 1024, LAYOUT_SW128, 0));
       const uint64_t bdesc_hi = make_smem_desc(0, 16, 1024, LAYOUT_SW128, 0);
       long long t0 = clock64();
       for (int r = 0; r < p.reps; r += 4) {
@@ -363,6 +364,9 @@ int main(int argc, char** argv) {
     cases.push_back({"kmajor", {0, N, 128, 0, 0, 128, 0, 0}});
   for (int s : {1, 3, 8, 9, 17, 66, 67, 127})
     for (int bo : {0, 1}) cases.push_back({"kmajor_shift", {0, 64, 128, s, bo, 256, 0, 0}});
+  // 8-row groups of A every `sbo` rows (SBO = sbo * 128 B): a (h+2) x (w+2) halo patch read in place, tap = row shift
+  for (int sbo : {10, 12, 16, 9})
+    for (int s : {0, 1, 11, 22}) cases.push_back({"kmajor_sbo", {0, 64, 128, s, 0, 256, sbo, 0}});
   // ---- MN-major ----
   for (int N : {32, 64, 128}) cases.push_back({"mnmajor_sw128", {1, N, 128, 0, 0, 128, 0, 0}});
   for (int s : {1, 3, 8, 9, 17, 67})
@@ -389,7 +393,7 @@ int main(int argc, char** argv) {
         for (int n = 0; n < p.N; ++n) {
           double acc = 0;
           for (int k = 0; k < p.K; ++k)
-            acc += (double)hA[(size_t)(m + p.shift) * p.K + k] * hB[(size_t)n * p.K + k];
+            acc += (double)hA[(size_t)((p.reps ? (m / 8) * p.reps + (m % 8) : m) + p.shift) * p.K + k] * hB[(size_t)n * p.K + k];
           ref[m * p.N + n] = (float)acc;
         }
     } else {
@@ -419,7 +423,7 @@ int main(int argc, char** argv) {
       // boxes limited to 256 rows; a_rows <= 264 -> clamp the box (rows beyond are never read when
       // shift + 128 <= box rows; the probe keeps shift + 128 <= a_rows <= 256+8, so clamp to 256)
       int box_rows = a_rows > 256 ? 256 : a_rows;
-      if (p.shift + 128 > box_rows) {
+      if (p.shift + (p.reps ? 15 * p.reps + 8 : 128) > box_rows) {
         printf("%s: bad config\n", cs.name);
         continue;
       }
@@ -452,6 +456,7 @@ int main(int argc, char** argv) {
       maxerr = fmax(maxerr, fabs((double)out[i] - ref[i]));
       maxref = fmax(maxref, fabs((double)ref[i]));
     }
+    if (p.mode == 0 && p.reps) printf("[sbo rows %d] ", p.reps);
     printf("%-22s N=%3d shift=%3d bo=%d : %s maxerr=%.4g (maxref %.3g) timeout=%d\n", cs.name, p.N,
            p.shift, p.base_off, (maxerr < 1e-2 * fmax(1.0, maxref) / 10 && !herr) ? "PASS" : "FAIL",
            maxerr, maxref, herr);
@@ -500,7 +505,7 @@ int main(int argc, char** argv) {
       for (int N : {16, 32, 64, 128}) {
           if (!shift_sweep && shift) continue;
           if (shift_sweep && (nissue != 2 || N == 16)) continue;
-          Params p = {3, N, 0, shift, 0, nissue, 4096, 0};
+          Params p = {3, N, (argc > 3 ? atoi(argv[3]) : 0), shift, 0, nissue, 4096, 0};
           CK(cudaMemset(derr, 0, sizeof(int)));
           CK(cudaMemset(dcyc, 0, 1024 * sizeof(long long)));
           probe_kernel<<<148, 128, SMEM>>>(dummy, dummy, p, dD, dcyc, derr);

@@ -144,6 +144,7 @@ _SIGNATURES = {
     "b200_conv3x3_thin_wgrad": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "b200_bn_stats": [_P, _P, _L, _I, _P],
     "b200_bn_finalize": [_P, _P, _P, _P, _L, _I, _F, _F, _P],
+    "b200_bn_stats_finalize": [_P, _P, _P, _P, _P, _L, _I, _F, _F, _P],
     "b200_bn_apply_lrelu": [_P, _P, _P, _P, _P, _L, _I, _F, _P],
     "b200_bn_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
     "b200_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P],

@@ -126,18 +126,19 @@ __device__ __forceinline__ bool det_arrive_last(unsigned* counter, unsigned nblk
 // Deterministic cross-block sum in two levels (a single last block adding nblk x nout partials would be a
 // multi-microsecond serial tail): the blocks form groups of kDetGroup; the last block of a group to arrive adds the
 // group's partials (contiguous in memory: part is OUTPUT-major, part[k * nblk + b]) in block order into
-// gpart[k * ngrp + g]; the last GROUP to finish adds the group sums in group order and calls out(k, total).
+// gpart[k * ngrp + g]; the last GROUP to finish adds the group sums in group order and calls out(k, total);
+// returns true (block-uniform) in that one block.
 // counters: 1 + ngrp words (self-resetting).  Every block of the grid must call it (blockDim.x = 256).
 constexpr int kDetGroup = 16;
 __host__ __device__ __forceinline__ int det_groups(int nblk) { return (nblk + kDetGroup - 1) / kDetGroup; }
 
 template <typename F>
-__device__ __forceinline__ void det_reduce(const float* __restrict__ part, float* __restrict__ gpart,
+__device__ __forceinline__ bool det_reduce(const float* __restrict__ part, float* __restrict__ gpart,
                                            unsigned* counters, unsigned nblk, int nout, F&& out) {
   const unsigned grp = blockIdx.x / kDetGroup, ngrp = det_groups((int)nblk);
   const unsigned g0 = grp * kDetGroup;
   const unsigned members = (nblk - g0) < (unsigned)kDetGroup ? (nblk - g0) : (unsigned)kDetGroup;
-  if (!det_arrive_last(counters + 1 + grp, members)) return;
+  if (!det_arrive_last(counters + 1 + grp, members)) return false;
   for (int k = threadIdx.x; k < nout; k += blockDim.x) {
     const float* row = part + (size_t)k * nblk + g0;
     float t = 0.f;
@@ -145,7 +146,7 @@ __device__ __forceinline__ void det_reduce(const float* __restrict__ part, float
     for (unsigned i = 0; i < members; ++i) t += row[i];
     gpart[(size_t)k * ngrp + grp] = t;
   }
-  if (!det_arrive_last(counters, ngrp)) return;
+  if (!det_arrive_last(counters, ngrp)) return false;
   for (int k = threadIdx.x; k < nout; k += blockDim.x) {
     const float* row = gpart + (size_t)k * ngrp;
     float t = 0.f;
@@ -153,6 +154,7 @@ __device__ __forceinline__ void det_reduce(const float* __restrict__ part, float
     for (unsigned g = 0; g < ngrp; ++g) t += row[g];
     out(k, t);
   }
+  return true;   // block-uniform: this block produced the totals
 }
 #endif
 

@@ -37,6 +37,23 @@ inline int grid_for(long long work_items, int threads, int max_blocks = 148 * 16
 
 // ------------------------------------------------------------------ BatchNorm
 // Each thread owns one 8-channel vector lane (c/8 lanes per pixel) and strides over pixels.
+// per-channel statistics -> mean / invstd (+ running statistics, unbiased variance, like nn.BatchNorm2d)
+__device__ __forceinline__ void bn_finalize_channel(const float* stats, float* mean_invstd, float* running_mean,
+                                                    float* running_var, long long npix, int c, float momentum,
+                                                    float eps, int ch) {
+  const double n = (double)npix;
+  const double mean = stats[ch] / n;
+  double var = stats[c + ch] / n - mean * mean;
+  if (var < 0) var = 0;
+  mean_invstd[ch] = (float)mean;
+  mean_invstd[c + ch] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    const double unbiased = npix > 1 ? var * n / (n - 1.0) : var;
+    running_mean[ch] = (float)((1.0 - momentum) * running_mean[ch] + momentum * mean);
+    running_var[ch] = (float)((1.0 - momentum) * running_var[ch] + momentum * unbiased);
+  }
+}
+
 // blockDim = 256; lanes_per_pix = c/8 must divide 256 or be a multiple handled by the loop.
 template <int MODE>  // 0: stats of z ; 1: bwd reduce (sum dbn, sum dbn*zhat)
 __global__ void bn_reduce_kernel(const __nv_bfloat16* __restrict__ z,
@@ -45,7 +62,9 @@ __global__ void bn_reduce_kernel(const __nv_bfloat16* __restrict__ z,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float* __restrict__ sums, long long npix, int c, float slope,
                                  float* __restrict__ part, unsigned* __restrict__ counter,
-                                 float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                 float* __restrict__ fin_mean_invstd, float* __restrict__ running_mean,
+                                 float* __restrict__ running_var, float momentum, float eps) {
   pdl_trigger();
   pdl_wait();
   const int vec_per_pix = c / 8;
@@ -120,7 +139,7 @@ __global__ void bn_reduce_kernel(const __nv_bfloat16* __restrict__ z,
     part[(size_t)k * gridDim.x + blockIdx.x] = t;
   }
   // deterministic two-level grid reduction (common.cuh)
-  det_reduce(part, part + (size_t)2 * c * gridDim.x, counter, gridDim.x, 2 * c, [&](int k, float t) {
+  const bool fin = det_reduce(part, part + (size_t)2 * c * gridDim.x, counter, gridDim.x, 2 * c, [&](int k, float t) {
     sums[k] = t;
     // MODE 1: sums[0..c) = sum dbn = d(beta), sums[c..2c) = sum dbn * zhat = d(gamma): accumulated here instead of
     // two extra launches per layer
@@ -132,6 +151,13 @@ __global__ void bn_reduce_kernel(const __nv_bfloat16* __restrict__ z,
       }
     }
   });
+  if (MODE == 0 && fin && fin_mean_invstd) {
+    // the block that produced the totals also turns them into mean / invstd and the running statistics
+    // (same arithmetic as bn_finalize_kernel): one launch less per BatchNorm layer
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x)
+      bn_finalize_channel(sums, fin_mean_invstd, running_mean, running_var, npix, c, momentum, eps, ch);
+  }
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, float* __restrict__ mean_invstd,
@@ -141,17 +167,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, float* __res
   pdl_wait();
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
-  const double n = (double)npix;
-  const double mean = stats[ch] / n;
-  double var = stats[c + ch] / n - mean * mean;
-  if (var < 0) var = 0;
-  mean_invstd[ch] = (float)mean;
-  mean_invstd[c + ch] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean) {
-    const double unbiased = npix > 1 ? var * n / (n - 1.0) : var;
-    running_mean[ch] = (float)((1.0 - momentum) * running_mean[ch] + momentum * mean);
-    running_var[ch] = (float)((1.0 - momentum) * running_var[ch] + momentum * unbiased);
-  }
+  bn_finalize_channel(stats, mean_invstd, running_mean, running_var, npix, c, momentum, eps, ch);
 }
 
 template <int MODE>  // 0: fwd apply+lrelu ; 1: bwd apply (dz)
@@ -519,15 +535,28 @@ typedef __nv_bfloat16 bf16;
 
 extern "C" {
 
-int b200_bn_stats(const void* z, float* stats, int64_t npix, int32_t c, b200_stream_t stream) {
+static int bn_stats_launch(const void* z, float* stats, float* mean_invstd, float* running_mean, float* running_var,
+                           int64_t npix, int32_t c, float momentum, float eps, b200_stream_t stream) {
   B200_REQUIRE(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "b200_bn_stats: c/8 must be a power of two <= 256 (c=%d)", c);
   const int grid = bn_grid(npix, c, 4, 148 * 2);   // the last block adds the per-block partials: keep them few
   DetScratch ds;
   if (det_scratch(&ds, (size_t)(grid + det_groups(grid)) * 2 * c, 1 + det_groups(grid))) return 1;
-  ::b200::launch_kernel(bn_reduce_kernel<0>, grid, 256, 16 * 256 * sizeof(float), as_stream(stream), 
-      (const bf16*)z, nullptr, nullptr, nullptr, nullptr, stats, npix, c, 0.f, ds.part, ds.counters, nullptr, nullptr);
+  ::b200::launch_kernel(bn_reduce_kernel<0>, grid, 256, 16 * 256 * sizeof(float), as_stream(stream),
+      (const bf16*)z, nullptr, nullptr, nullptr, nullptr, stats, (long long)npix, c, 0.f, ds.part, ds.counters, nullptr, nullptr,
+      mean_invstd, running_mean, running_var, momentum, eps);
   B200_LAUNCH_CHECK();
   return 0;
+}
+
+int b200_bn_stats(const void* z, float* stats, int64_t npix, int32_t c, b200_stream_t stream) {
+  return bn_stats_launch(z, stats, nullptr, nullptr, nullptr, npix, c, 0.f, 0.f, stream);
+}
+
+int b200_bn_stats_finalize(const void* z, float* stats, float* mean_invstd, float* running_mean,
+                           float* running_var, int64_t npix, int32_t c, float momentum, float eps,
+                           b200_stream_t stream) {
+  B200_REQUIRE(mean_invstd != nullptr, "b200_bn_stats_finalize: mean_invstd is required");
+  return bn_stats_launch(z, stats, mean_invstd, running_mean, running_var, npix, c, momentum, eps, stream);
 }
 
 int b200_bn_finalize(const float* stats, float* mean_invstd, float* running_mean,
@@ -557,7 +586,8 @@ int b200_bn_bwd_reduce(const void* z, const void* da, const float* mean_invstd, 
   DetScratch ds;
   if (det_scratch(&ds, (size_t)(grid + det_groups(grid)) * 2 * c, 1 + det_groups(grid))) return 1;
   ::b200::launch_kernel(bn_reduce_kernel<1>, grid, 256, 16 * 256 * sizeof(float), as_stream(stream), 
-      (const bf16*)z, (const bf16*)da, mean_invstd, gamma, beta, sums, npix, c, slope, ds.part, ds.counters, dgamma, dbeta);
+      (const bf16*)z, (const bf16*)da, mean_invstd, gamma, beta, sums, npix, c, slope, ds.part, ds.counters, dgamma, dbeta,
+      nullptr, nullptr, nullptr, 0.f, 0.f);
   B200_LAUNCH_CHECK();
   return 0;
 }

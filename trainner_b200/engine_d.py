@@ -92,9 +92,8 @@ class DiscriminatorEngine:
                 add_igemm(f, d, ctx.A[i], L.w_fwd, L.bias, y=ctx.Z[i])
                 npix = N * ho * ho
                 if train:
-                    f.add(lib.b200_bn_stats, P(ctx.Z[i]), P(ctx.stats[i]), npix, L.cout)
-                    f.add(lib.b200_bn_finalize, P(ctx.stats[i]), P(ctx.mi[i]), P(bn.running_mean),
-                          P(bn.running_var), npix, L.cout, float(bn.momentum), float(bn.eps))
+                    f.add(lib.b200_bn_stats_finalize, P(ctx.Z[i]), P(ctx.stats[i]), P(ctx.mi[i]),
+                          P(bn.running_mean), P(bn.running_var), npix, L.cout, float(bn.momentum), float(bn.eps))
                 f.add(lib.b200_bn_apply_lrelu, P(ctx.Z[i]), P(ctx.mi[i]), P(bn.weight), P(bn.bias),
                       P(ctx.A[i + 1]), npix, L.cout, SL)
             f.add(lib.b200_nhwc_bf16_to_nchw_f32, P(ctx.A[-1]), P(ctx.feat), N, cl, ctx.hf, ctx.hf, cl, 0)

@@ -158,9 +158,8 @@ def batchnorm_lrelu_train(z, gamma, beta, running_mean=None, running_var=None, m
     mi = torch.empty(2 * c, dtype=torch.float32, device=z.device)
     a = torch.empty_like(z)
     s = stream_ptr()
-    _lib.check(lib.b200_bn_stats(_p(z), _p(stats), npix, c, s), "bn_stats")
-    _lib.check(lib.b200_bn_finalize(_p(stats), _p(mi), _p(running_mean), _p(running_var), npix, c, momentum, eps,
-                                    s), "bn_finalize")
+    _lib.check(lib.b200_bn_stats_finalize(_p(z), _p(stats), _p(mi), _p(running_mean), _p(running_var), npix, c,
+                                          momentum, eps, s), "bn_stats_finalize")
     _lib.check(lib.b200_bn_apply_lrelu(_p(z), _p(mi), _p(gamma), _p(beta), _p(a), npix, c, slope, s), "bn_apply")
     return a, mi
 
