@@ -10,6 +10,8 @@ SHAPES = [  # (n, h, w, cin, cout)
     (16, 256, 256, 64, 64), (16, 128, 128, 64, 128), (16, 128, 128, 128, 128), (16, 64, 64, 128, 256),
     (16, 64, 64, 256, 256), (16, 32, 32, 256, 512), (16, 32, 32, 512, 512), (16, 16, 16, 512, 512),
 ]
+if len(sys.argv) > 1:
+    SHAPES = [SHAPES[int(a)] for a in sys.argv[1:]]
 torch.manual_seed(0)
 for n, h, w, cin, cout in SHAPES:
     x = (torch.randn(n, h, w, cin, device="cuda") * 0.5).to(torch.bfloat16)

@@ -46,6 +46,14 @@ struct IgemmParams {
   int stages;
   uint32_t b_bytes;  // BN * 128 (TMA transaction bytes of one B slot)
   uint32_t stage_bytes;
+  // staged epilogue of the 256-row kernel: finished 64-channel slabs go through a SW128 staging buffer and leave as
+  // TMA tile stores (out_map[parity class or 2x2 replica]); 0 = per-thread 16-byte stores
+  int tma_store;
+  int st_bufs;                // staging buffers per 128-row half (1 or 2), 16 KB each
+  uint32_t st_off;            // byte offset of the staging area behind the operand ring
+  int st_dy, st_dn;           // output-tile rows / images between the two halves
+  int dbg;                    // B200_IGEMM_DBG (experiments): 1 skip the epilogue's global traffic
+  CUtensorMap out_map[4];
   // output placement
   __nv_bfloat16* out;
   long long o_sn, o_sy, o_sx;
@@ -411,6 +419,12 @@ __device__ __forceinline__ void epi256_store(const IgemmParams& p, const uint32_
   }
 }
 
+// EPI = 0: general epilogue (residuals, accumulate, partial channel blocks, direct or staged stores).
+// EPI = 1 / 2: the straight-line epilogue of the common case -- staged TMA stores, BN a multiple of 64, only
+// bias / alpha / LeakyReLU (1) plus the activation-derivative mask (2).  The general code evaluates every feature
+// flag per 8-channel group; with two epilogue warps per scheduler nothing hides those dependent branches and loads,
+// and the epilogue (not the tensor pipe) set the pace of every layer (profiles/r02_igemm_epilogue.txt).
+template <int EPI>
 __global__ void __launch_bounds__(kThreads256, 1)
 conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -418,6 +432,7 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float sbias[EPI ? 256 : 4];   // this tile's bias slice (EPI != 0)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -529,10 +544,11 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
     const int in_ = m / (p.tw * p.th);
     int acc = 0;
     uint32_t acc_phase = 0;
+    int st_count = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       const int x = tc.x0 + ix, y = tc.y0 + iy, n = tc.n0 + in_;
-      const bool valid = (x < p.Wo) && (y < p.Ho) && (n < p.Nimg);
+      const bool valid = (x < p.Wo) && (y < p.Ho) && (n < p.Nimg) && !(p.dbg & 1);
       const int cy_ = tc.cls >> 1, cx_ = tc.cls & 1;   // parity offsets of a merged launch (0 otherwise)
       const long long pix_lin = ((long long)n * p.aux_h + (y * p.aux_my + p.aux_oy + cy_)) * p.aux_w +
                                 (x * p.aux_mx + p.aux_ox + cx_);
@@ -544,11 +560,90 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
       const uint32_t t_row = tmem + ((uint32_t)(quad * 32) << 16) + acc * 2 * p.acc_cols + half * p.acc_cols;
       const int cb = tc.nb * p.BN;
       int c0 = 0;
+      if constexpr (EPI != 0) {
+        const int m_local = quad * 32 + lane;
+        const bool issuer = (quad == 0) && (lane == 0);
+        const int ty = tc.y0 + half * p.st_dy, tn_ = tc.n0 + half * p.st_dn;
+        // bias slice of this tile -> shared memory (one copy for both halves)
+        named_bar_sync(3, 256);   // everyone is done with the previous tile's slice
+        {
+          const int e = half * 128 + m_local;
+          if (e < p.BN) sbias[e] = (p.bias && cb + e < p.Cout) ? __ldg(p.bias + cb + e) : 0.f;
+        }
+        named_bar_sync(3, 256);
+        const float alpha = p.alpha, slope = p.slope, mslope = p.mask_slope;
+        const bool act = p.act != 0;
+        const __nv_bfloat16* mrow = (EPI == 2 && valid) ? p.mask + pix_lin * p.mask_c + p.mask_coff : nullptr;
+        uint32_t r[2][32];
+        tmem_ld_32x32b_x32(t_row, r[0]);
+        tmem_ld_32x32b_x32(t_row + 32, r[1]);
+        for (; c0 < p.BN; c0 += 64) {
+          const int buf = st_count % p.st_bufs;
+          ++st_count;
+          uint8_t* sbuf = smem + p.st_off + (size_t)(half * p.st_bufs + buf) * (128 * 128);
+          uint4 mk[8];
+          if (EPI == 2) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const int c = cb + c0 + g * 8;
+              mk[g] = (mrow && c >= p.mask_lo && c < p.mask_hi) ? __ldg(reinterpret_cast<const uint4*>(mrow + c))
+                                                               : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+            }
+          }
+          if (issuer) {   // the store that last read this staging buffer has drained it
+            if (p.st_bufs == 2) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+          }
+          if (half == 0) named_bar_sync(1, 128); else named_bar_sync(2, 128);
+          tmem_ld_wait();
+          const uint32_t srow = smem_u32(sbuf) + (uint32_t)m_local * 128;
+          const int sx = m_local & 7;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float v[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(&sbias[c0 + g * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&sbias[c0 + g * 8 + 4]);
+            const uint32_t* a = &r[g >> 2][(g & 3) * 8];
+            v[0] = (__uint_as_float(a[0]) + b0.x) * alpha; v[1] = (__uint_as_float(a[1]) + b0.y) * alpha;
+            v[2] = (__uint_as_float(a[2]) + b0.z) * alpha; v[3] = (__uint_as_float(a[3]) + b0.w) * alpha;
+            v[4] = (__uint_as_float(a[4]) + b1.x) * alpha; v[5] = (__uint_as_float(a[5]) + b1.y) * alpha;
+            v[6] = (__uint_as_float(a[6]) + b1.z) * alpha; v[7] = (__uint_as_float(a[7]) + b1.w) * alpha;
+            if (act) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * slope;
+            }
+            if (EPI == 2) {
+              float mf[8];
+              unpack8(mk[g], mf);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = mf[j] > 0.f ? v[j] : v[j] * mslope;
+            }
+            const uint4 o = pack8(v);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)((g ^ sx) << 4)), "r"(o.x),
+                         "r"(o.y), "r"(o.z), "r"(o.w)
+                         : "memory");
+          }
+          if (c0 + 64 < p.BN) {   // next slab's accumulators: in flight while this slab is stored
+            tmem_ld_32x32b_x32(t_row + c0 + 64, r[0]);
+            tmem_ld_32x32b_x32(t_row + c0 + 96, r[1]);
+          }
+          fence_proxy_async_smem();
+          if (half == 0) named_bar_sync(1, 128); else named_bar_sync(2, 128);
+          if (issuer && !(p.dbg & 1)) {
+            const int ch = p.o_coff + cb + c0;
+            if (p.upsample) {
+#pragma unroll
+              for (int rep = 0; rep < 4; ++rep) tma_store_4d(&p.out_map[rep], sbuf, ch, tc.x0, ty, tn_);
+            } else {
+              tma_store_4d(&p.out_map[tc.cls], sbuf, ch, tc.x0, ty, tn_);
+            }
+            bulk_commit_group();
+          }
+        }
+      } else {
       for (; c0 + 32 <= p.BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c0, r);
-        EpiLoads256<32> L;
-        if (valid) epi256_load<32>(p, L, cb + c0, pix_lin, out_px);
+        EpiLoads256<32> L;        if (valid) epi256_load<32>(p, L, cb + c0, pix_lin, out_px);
         tmem_ld_wait();
         if (valid) epi256_store<32>(p, r, L, cb + c0, out_px);
       }
@@ -560,6 +655,7 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
         tmem_ld_wait();
         if (valid) epi256_store<16>(p, r, L, cb + c0, out_px);
       }
+      }   // EPI == 0
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -571,6 +667,7 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
       }
     }
   }
+  if (p.tma_store && warp >= 3 && (warp & 3) == 0 && lane == 0) bulk_wait_group<0>();   // staging buffers drained
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
@@ -604,7 +701,10 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
 
   const int kSmemBytes = 200 * 1024;
   B200_ENSURE_SMEM(conv_igemm_kernel, kSmemBytes);
-  B200_ENSURE_SMEM(conv_igemm256_kernel, kSmemBytes);
+  const int kSmem256 = 225 * 1024;   // the 256-row kernel also stages its output tiles
+  B200_ENSURE_SMEM(conv_igemm256_kernel<0>, kSmem256);
+  B200_ENSURE_SMEM(conv_igemm256_kernel<1>, kSmem256);
+  B200_ENSURE_SMEM(conv_igemm256_kernel<2>, kSmem256);
 
   IgemmParams p;
   memset(&p, 0, sizeof(p));
@@ -685,6 +785,30 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
   p.stages = (kSmemBytes - 2048) / (int)p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   B200_REQUIRE(p.stages >= 2, "b200_conv_igemm: not enough shared memory for 2 stages");
+  static const int igemm_dbg = getenv("B200_IGEMM_DBG") ? atoi(getenv("B200_IGEMM_DBG")) : 0;
+  p.dbg = igemm_dbg;
+  // straight-line epilogue with staged TMA tile stores (conv_igemm256_kernel<1 / 2>): whole 64-channel slabs, no
+  // residual / accumulate operands
+  static const bool fast_epi_enabled = [] {
+    const char* e = getenv("B200_IGEMM_FAST_EPI");
+    return !(e && e[0] == '0');
+  }();
+  p.tma_store = use256 && fast_epi_enabled && BN % 64 == 0 && !res1 && !res2 && !d->accumulate;
+  if (p.tma_store) {
+    const int kSlab = 128 * 128;   // one half's 64-channel slab
+    p.st_bufs = 2;
+    int st = (kSmem256 - 1024 - 2 * p.st_bufs * kSlab) / (int)p.stage_bytes;
+    if (st < 3) {
+      p.st_bufs = 1;
+      st = (kSmem256 - 1024 - 2 * p.st_bufs * kSlab) / (int)p.stage_bytes;
+    }
+    if (st < 2) {
+      p.tma_store = 0;
+    } else {
+      p.stages = st > kMaxStages ? kMaxStages : st;
+      p.st_off = (uint32_t)p.stages * p.stage_bytes;
+    }
+  }
 
   // ---- tensor maps
   {
@@ -707,6 +831,26 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
   }
   // ---- output placement
   p.out = reinterpret_cast<__nv_bfloat16*>(y);
+  if (p.tma_store) {
+    // strided views of the output, one per parity class / 2x2 replica: [channels, Wo, Ho, N] at pitch (mul_x, mul_y)
+    const int mul_y = d->upsample2x ? 2 : (d->out_mul_y ? d->out_mul_y : 1);
+    const int mul_x = d->upsample2x ? 2 : (d->out_mul_x ? d->out_mul_x : 1);
+    const int off_y = d->upsample2x ? 0 : d->out_off_y, off_x = d->upsample2x ? 0 : d->out_off_x;
+    const int nmaps = (ncls == 4 || d->upsample2x) ? 4 : 1;
+    const int half_th = p.tn >= 2 ? p.th : p.th / 2, half_tn = p.tn >= 2 ? p.tn / 2 : 1;
+    p.st_dy = p.tn >= 2 ? 0 : p.th / 2;
+    p.st_dn = p.tn >= 2 ? p.tn / 2 : 0;
+    for (int k = 0; k < nmaps; ++k) {
+      const long long base = ((long long)(off_y + (k >> 1)) * d->w_buf + (off_x + (k & 1))) * d->cy;
+      uint64_t dims[4] = {(uint64_t)(d->cout_off + d->cout), (uint64_t)d->w_out, (uint64_t)d->h_out, (uint64_t)d->n};
+      uint64_t strides[3] = {(uint64_t)mul_x * d->cy * 2, (uint64_t)mul_y * d->w_buf * d->cy * 2,
+                             (uint64_t)d->h_buf * d->w_buf * d->cy * 2};
+      uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)half_th, (uint32_t)half_tn};
+      if (make_tensor_map(&p.out_map[k], reinterpret_cast<const __nv_bfloat16*>(y) + base, 4, dims, strides, box,
+                          nullptr, CU_TENSOR_MAP_SWIZZLE_128B))
+        return 1;
+    }
+  }
   p.o_sx = d->cy;
   p.o_sy = (long long)d->w_buf * d->cy;
   p.o_sn = (long long)d->h_buf * d->w_buf * d->cy;
@@ -746,9 +890,14 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
   p.mask_slope = d->mask_slope;
 
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-  if (use256)
-    ::b200::launch_kernel(conv_igemm256_kernel, grid, kThreads256, smem, as_stream(stream), p);
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (p.tma_store ? 2 * (size_t)p.st_bufs * 128 * 128 : 0);
+  const bool fast = p.tma_store != 0;
+  if (use256 && fast && mask)
+    ::b200::launch_kernel(conv_igemm256_kernel<2>, grid, kThreads256, smem, as_stream(stream), p);
+  else if (use256 && fast)
+    ::b200::launch_kernel(conv_igemm256_kernel<1>, grid, kThreads256, smem, as_stream(stream), p);
+  else if (use256)
+    ::b200::launch_kernel(conv_igemm256_kernel<0>, grid, kThreads256, smem, as_stream(stream), p);
   else
     ::b200::launch_kernel(conv_igemm_kernel, grid, kThreads, smem, as_stream(stream), p);
   B200_LAUNCH_CHECK();

@@ -216,9 +216,6 @@ __device__ __forceinline__ void tma_load_3d_mcast(void* smem, const CUtensorMap*
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
       : "memory");
 }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // A stage may be issued in two parts: part 0 = the 32 (j = 4: 64) accumulator columns that stage j COMPLETES, part 1 =
 // the columns of the later convs, so that the epilogue / halo exchange of the completed columns overlaps part 1 on the
