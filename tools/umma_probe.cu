@@ -169,12 +169,15 @@ probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int nissue = p.a_rows > 0 ? p.a_rows : 1;
     if (warp < nissue) {
       // warp-uniform issue loop: operands live in uniform registers, one elected lane issues.
-      const uint32_t idesc = make_idesc_bf16(128, p.N, p.a_mn, 0);
+      // a_mn bit 0: A MN-major, bit 1: B MN-major (the wgrad formulation: both operands pixel-major)
+      const uint32_t idesc = make_idesc_bf16(128, p.N, p.a_mn & 1, (p.a_mn >> 1) & 1);
       const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-      const uint32_t a_kstep = p.a_mn ? 16 * 128 : 32;
-      const uint64_t adesc_hi = p.a_mn ? (make_smem_desc(0, 8192, 1024, LAYOUT_SW128, 0))
+      const uint32_t a_kstep = (p.a_mn & 1) ? 16 * 128 : 32;
+      const uint32_t b_kstep = (p.a_mn & 2) ? 16 * 128 : 32;
+      const uint64_t adesc_hi = (p.a_mn & 1) ? (make_smem_desc(0, 8192, 1024, LAYOUT_SW128, 0))
                                        : (make_smem_desc(0, 16, p.K ? p.K * 128 : 1024, LAYOUT_SW128, 0));
-      const uint64_t bdesc_hi = make_smem_desc(0, 16, 1024, LAYOUT_SW128, 0);
+      const uint64_t bdesc_hi = (p.a_mn & 2) ? make_smem_desc(0, 8192, 1024, LAYOUT_SW128, 0)
+                                             : make_smem_desc(0, 16, 1024, LAYOUT_SW128, 0);
       long long t0 = clock64();
       for (int r = 0; r < p.reps; r += 4) {
         const int st = (r >> 2) & 3;
@@ -183,7 +186,7 @@ probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             uint64_t ad = adesc_hi | (uint64_t)(((a_addr + k * a_kstep) >> 4) & 0x3FFF);
-            uint64_t bd = bdesc_hi | (uint64_t)(((b_addr + k * 32) >> 4) & 0x3FFF);
+            uint64_t bd = bdesc_hi | (uint64_t)(((b_addr + k * b_kstep) >> 4) & 0x3FFF);
             umma_f16(tmem + warp * 128 + ((p.base_off && (k & 1)) ? 64 : 0), ad, bd, idesc, (r | k) > 1);
           }
         }
@@ -505,7 +508,7 @@ int main(int argc, char** argv) {
       for (int N : {16, 32, 64, 128}) {
           if (!shift_sweep && shift) continue;
           if (shift_sweep && (nissue != 2 || N == 16)) continue;
-          Params p = {3, N, (argc > 3 ? atoi(argv[3]) : 0), shift, 0, nissue, 4096, 0};
+          Params p = {3, N, (argc > 3 ? atoi(argv[3]) : 0), shift, 0, nissue, 4096, (argc > 4 ? atoi(argv[4]) : 0)};
           CK(cudaMemset(derr, 0, sizeof(int)));
           CK(cudaMemset(dcyc, 0, 1024 * sizeof(long long)));
           probe_kernel<<<148, 128, SMEM>>>(dummy, dummy, p, dD, dcyc, derr);

@@ -204,6 +204,56 @@ wgrad_rdb_kernel(const __grid_constant__ RdbItemParams p) {
       mbar_wait(&tfull_bar, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem + ((uint32_t)(quad * 32) << 16);
+      if (p.ws && nf == 64 && gc == 32) {
+        // Split-workspace path, specialised for the (64, 32) RDB the slab layout assumes: no per-element index
+        // arithmetic (the generic loop below spends ~90 k cycles per item on divisions and branches, and this
+        // epilogue is NOT overlapped -- one accumulator set fills TMEM), x32 TMEM loads issued one block ahead.
+        float* slab = p.ws + ((size_t)slice * p.n_rdb + r) * kSlabFloats;
+        const int nblk = 3 * (N / 32);          // 32-column blocks over the three taps
+        uint32_t v0[32], v1[32];
+        auto issue = [&](uint32_t* dst, int b) {
+          tmem_ld_32x32b_x32(t_row + (b / (N / 32)) * N + (b % (N / 32)) * 32, dst);
+        };
+        auto emit = [&](const uint32_t* vv, int b) {
+          const int t = b / (N / 32), c0 = (b % (N / 32)) * 32;
+          const int tap = (dy + 1) * 3 + t;
+          if (type == 0) {            // row = ci < 128 ; block c0/32 = conv k (cout 32, cin 64 + 32 k)
+            const int k = c0 >> 5, cin_k = 64 + 32 * k;
+            if (row < cin_k) {
+              float* d = slab + slab_off(k, 64, 32) + (size_t)(tap * 32) * cin_k + row;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) d[(size_t)j * cin_k] = __uint_as_float(vv[j]);
+            }
+          } else if (type == 1) {     // conv5: ci = row < 128, co = c0 + j
+            float* d = slab + slab_off(4, 64, 32) + (size_t)(tap * 64 + c0) * 192 + row;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) d[(size_t)j * 192] = __uint_as_float(vv[j]);
+          } else {                    // row = co' in [dY3 | dY4 | dO], columns = ci - 128
+            if (row >= 64) {          // dO -> conv5, ci = 128 + c0 + j
+              float4* d = reinterpret_cast<float4*>(slab + slab_off(4, 64, 32) + (size_t)(tap * 64 + row - 64) * 192 + 128 + c0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                d[j] = make_float4(__uint_as_float(vv[4 * j]), __uint_as_float(vv[4 * j + 1]),
+                                   __uint_as_float(vv[4 * j + 2]), __uint_as_float(vv[4 * j + 3]));
+            } else if (row >= 32 && c0 == 0) {   // dY4 -> conv4 (cin 160): ci = 128 .. 159
+              float4* d = reinterpret_cast<float4*>(slab + slab_off(3, 64, 32) + (size_t)(tap * 32 + row - 32) * 160 + 128);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                d[j] = make_float4(__uint_as_float(vv[4 * j]), __uint_as_float(vv[4 * j + 1]),
+                                   __uint_as_float(vv[4 * j + 2]), __uint_as_float(vv[4 * j + 3]));
+            }                         // dY3 -> conv3 has only 128 inputs: nothing here
+          }
+        };
+        issue(v0, 0);
+        for (int b = 0; b < nblk; b += 2) {   // nblk is even (6 or 12): static ping-pong, no local-memory arrays
+          tmem_ld_wait();
+          issue(v1, b + 1);
+          emit(v0, b);
+          tmem_ld_wait();
+          if (b + 2 < nblk) issue(v0, b + 2);
+          emit(v1, b + 1);
+        }
+      } else
       for (int t = 0; t < 3; ++t) {
         const int tap = (dy + 1) * 3 + t;
         for (int c0 = 0; c0 < N; c0 += 16) {
