@@ -53,6 +53,7 @@ struct IgemmParams {
   uint32_t st_off;            // byte offset of the staging area behind the operand ring
   int st_dy, st_dn;           // output-tile rows / images between the two halves
   int dbg;                    // B200_IGEMM_DBG (experiments): 1 skip the epilogue's global traffic
+  long long* dbg_ptr;         // B200_IGEMM_DBG_PTR (tools/igemm_timeline.py): CTA 0 stamps clock64() per k-iteration
   CUtensorMap out_map[4];
   // output placement
   __nv_bfloat16* out;
@@ -469,6 +470,7 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
   if (warp == 0) {
     int stage = 0;
     uint32_t phase = 0;
+    int dbg_it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       for (int t0 = 0; t0 < p.ntaps; ++t0) {
@@ -478,6 +480,7 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
         const int wt = p.tap_w[t];
         for (int c = 0; c < p.k_chunks; ++c) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (p.dbg_ptr && blockIdx.x == 0 && lane == 0 && dbg_it < 64) p.dbg_ptr[128 + dbg_it++] = clock64();
           if (elect_one()) {
             uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
             mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
@@ -501,6 +504,7 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int dbg_it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
@@ -509,6 +513,8 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
       for (int it = 0; it < k_iters; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        const bool stamp = p.dbg_ptr && blockIdx.x == 0 && half == 0 && lane == 0 && dbg_it < 64;
+        if (stamp) p.dbg_ptr[2 * dbg_it] = clock64();
         const int nk = (c == p.k_chunks - 1) ? p.last_k16 : 4;
         const uint32_t a_addr = smem_base + stage * p.stage_bytes + half * kABytes;
         const uint32_t b_addr = smem_base + stage * p.stage_bytes + p.a_bytes;
@@ -522,6 +528,7 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
           if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
+        if (stamp) p.dbg_ptr[2 * dbg_it++ + 1] = clock64();
         if (++c == p.k_chunks) c = 0;
         if (++stage == p.stages) {
           stage = 0;
@@ -544,7 +551,7 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
     const int in_ = m / (p.tw * p.th);
     int acc = 0;
     uint32_t acc_phase = 0;
-    int st_count = 0;
+    int st_count = 0, st_tiles = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       const int x = tc.x0 + ix, y = tc.y0 + iy, n = tc.n0 + in_;
@@ -557,6 +564,8 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
                               (long long)(x * p.o_mx + p.o_ox + cx_) * p.o_sx;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      const bool estamp = p.dbg_ptr && blockIdx.x == 0 && warp == 3 && lane == 0 && st_tiles < 8;
+      if (estamp) p.dbg_ptr[256 + 2 * st_tiles] = clock64();
       const uint32_t t_row = tmem + ((uint32_t)(quad * 32) << 16) + acc * 2 * p.acc_cols + half * p.acc_cols;
       const int cb = tc.nb * p.BN;
       int c0 = 0;
@@ -656,6 +665,7 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
         if (valid) epi256_store<16>(p, r, L, cb + c0, out_px);
       }
       }   // EPI == 0
+      if (estamp) p.dbg_ptr[256 + 2 * st_tiles++ + 1] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -749,6 +759,10 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
       if (!(bn >= 64 && bn % 32 == 0 && d->cout % (bn / 2) == 0)) break;
     }
   }
+  static const bool igemm_debug = getenv("B200_IGEMM_DEBUG") != nullptr;
+  if (igemm_debug)
+    fprintf(stderr, "conv_igemm: cin %d cout %d %dx%dx%d taps %d x%d stride %d -> %d-row tile x BN %d (model %.0f cycles)\n",
+            d->cin, d->cout, d->n, d->h_out, d->w_out, d->ntaps, ncls, d->in_stride, best_rows, BN, best_cost);
   const bool use256 = best_rows == 256;
   int pixel_tiles = geometry(best_rows);
   p.BN = BN;
@@ -787,6 +801,9 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
   B200_REQUIRE(p.stages >= 2, "b200_conv_igemm: not enough shared memory for 2 stages");
   static const int igemm_dbg = getenv("B200_IGEMM_DBG") ? atoi(getenv("B200_IGEMM_DBG")) : 0;
   p.dbg = igemm_dbg;
+  static long long* const igemm_dbg_ptr =
+      getenv("B200_IGEMM_DBG_PTR") ? reinterpret_cast<long long*>(strtoull(getenv("B200_IGEMM_DBG_PTR"), nullptr, 0)) : nullptr;
+  p.dbg_ptr = igemm_dbg_ptr;
   // straight-line epilogue with staged TMA tile stores (conv_igemm256_kernel<1 / 2>): whole 64-channel slabs, no
   // residual / accumulate operands
   static const bool fast_epi_enabled = [] {
