@@ -454,27 +454,35 @@ wide_to_thin_mma_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
     }
     bfrag[i] = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
   }
+  // Persistent over 16 x 16 pixel tiles (weight fragments built once per CTA); the haloed input tile arrives through
+  // cp.async (zero fill outside the image): all of a thread's ~10 16-byte loads are in flight together instead of one
+  // dependent global load per loop iteration, which is what kept this HBM-bound kernel at 20 % of the HBM peak.
   const int tiles_x = (w + 15) / 16, tiles_y = (h + 15) / 16;
-  const int b = blockIdx.x / (tiles_x * tiles_y);
-  const int tr = blockIdx.x % (tiles_x * tiles_y);
-  const int x0 = (tr % tiles_x) * 16, y0 = (tr / tiles_x) * 16;
+  const int total_tiles = n * tiles_x * tiles_y;
   const int swz_mask = chunks >= 8 ? 7 : (chunks - 1);
+  const uint32_t tile_s = smem_addr(tile);
+  for (int tile_i = blockIdx.x; tile_i < total_tiles; tile_i += gridDim.x) {
+  const int b = tile_i / (tiles_x * tiles_y);
+  const int tr = tile_i % (tiles_x * tiles_y);
+  const int x0 = (tr % tiles_x) * 16, y0 = (tr / tiles_x) * 16;
+  __syncthreads();   // previous tile fully consumed (first pass: bfrag complete)
   for (int i = tid; i < 324 * chunks; i += 256) {
     const int ch = i % chunks, pix = i / chunks;
     const int px = pix % 18, py = pix / 18;
     const int gx = x0 + px - 1, gy = y0 + py - 1;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (gx >= 0 && gx < w && gy >= 0 && gy < h)
-      v = *reinterpret_cast<const uint4*>(x + (((size_t)b * h + gy) * w + gx) * cx + x_coff + ch * 8);
-    tile[pix * chunks + (ch ^ (px & swz_mask))] = v;
+    const bool in = gx >= 0 && gx < w && gy >= 0 && gy < h;
+    const __nv_bfloat16* src = in ? x + (((size_t)b * h + gy) * w + gx) * cx + x_coff + ch * 8 : x;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tile_s + (uint32_t)((pix * chunks + (ch ^ (px & swz_mask))) * 16)),
+                 "l"(src), "r"(in ? 16 : 0)
+                 : "memory");
   }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   float acc[2][4];
 #pragma unroll
   for (int r = 0; r < 2; ++r)
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
-  const uint32_t tile_s = smem_addr(tile);
   const int mi = lane >> 3, lr = lane & 7;
 #pragma unroll 1
   for (int tap = 0; tap < 9; ++tap) {
@@ -505,6 +513,7 @@ wide_to_thin_mma_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
       y[(((size_t)b * cs + co) * h + gy) * w + gx] = v * out_scale;
     }
   }
+  }   // tile loop
 }
 
 // ---------------------------------------------------------------- weight gradient, GEMM [64] x [px] x [CS*9 + 1]
@@ -722,7 +731,7 @@ int b200_conv3x3_wide_to_thin(const void* x, const float* w_oihw, const float* b
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
       msm_set = msm;
     }
-    ::b200::launch_kernel(wide_to_thin_mma_kernel, blocks_m, 256, msm, as_stream(stream), 
+    ::b200::launch_kernel(wide_to_thin_mma_kernel, (blocks_m < 4 * sm_count() ? blocks_m : 4 * sm_count()), 256, msm, as_stream(stream), 
         (const bf16*)x, w_oihw, bias, y, n, h, w, cw, cx, x_coff, cs, transpose_w, inv_std, out_scale);
     B200_LAUNCH_CHECK();
     return 0;
