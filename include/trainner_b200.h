@@ -67,6 +67,13 @@ typedef struct {
 int b200_conv_igemm(const b200_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                     const void* res1, const void* res2, const void* mask, void* y,
                     b200_stream_t stream);
+/* The same conv (no residual / mask / activation operands) that ALSO writes the BatchNorm partial statistics of
+ * its bf16-rounded output from the epilogue: stat_part is fp32 [2][cout][rows], rows = b200_conv_igemm_stat_rows(d)
+ * (0 when this shape is not served by the statistics epilogue -- use b200_bn_stats then; < 0 on error).
+ * Replaces the separate pass of nn.BatchNorm2d's batch statistics over the conv output (block.py:122).        */
+int b200_conv_igemm_stat_rows(const b200_conv_desc* d);
+int b200_conv_igemm_stats(const b200_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                          void* y, float* stat_part, b200_stream_t stream);
 
 /* 3x3 stride-1 pad-1 convolution on ZERO-BORDERED ("flat") activations, the trunk fast path.
  * Tensors are [n, h+2, w+2, c] NHWC bf16 whose 1-pixel border is zero and never written; with the
@@ -285,6 +292,12 @@ int b200_bn_finalize(const float* stats, float* mean_invstd, float* running_mean
 int b200_bn_stats_finalize(const void* z, float* stats, float* mean_invstd, float* running_mean,
                            float* running_var, int64_t npix, int32_t c, float momentum, float eps,
                            b200_stream_t stream);
+/* BatchNorm statistics from the conv epilogue instead of a pass over z: b200_conv_igemm_stats (below) writes one
+ * row of per-channel (sum, sum of squares) per 128-pixel half tile into part[2][c][rows]; this adds the rows in a
+ * fixed order and finishes like b200_bn_finalize.  rows = b200_conv_igemm_stat_rows(desc).                      */
+int b200_bn_partials_finalize(const float* part, int32_t rows, float* stats, float* mean_invstd,
+                              float* running_mean, float* running_var, int64_t npix, int32_t c, float momentum,
+                              float eps, b200_stream_t stream);
 int b200_bn_apply_lrelu(const void* z, const float* mean_invstd, const float* gamma,
                         const float* beta, void* a, int64_t npix, int32_t c, float slope,
                         b200_stream_t stream);

@@ -176,6 +176,51 @@ def test_batchnorm_lrelu(N, H, W, C):
     assert rel(dg, gamma.grad) < 2e-3 and rel(dbt, beta.grad) < 2e-3
 
 
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,s,p", [(8, 64, 64, 64, 128, 3, 1, 1), (8, 128, 128, 64, 64, 4, 2, 1),
+                                                   (3, 40, 44, 128, 256, 3, 1, 1), (16, 16, 16, 512, 512, 3, 1, 1)])
+def test_conv_igemm_stats_epilogue(N, H, W, Cin, Cout, k, s, p):
+    """BatchNorm batch statistics straight from the conv epilogue (conv_igemm EPI = 3: per-tile column sums of the
+    bf16-rounded outputs + b200_bn_partials_finalize) against a pass over the stored conv output
+    (b200_bn_stats_finalize) and against PyTorch; ragged tiles, stride 2, deterministic."""
+    import ctypes as C
+    from trainner_b200 import ops, _lib
+    from trainner_b200.runtime import make_conv_desc, taps_conv, stream_ptr, igemm_stat_rows
+    lib = _lib.lib
+    x = nhwc(rnd(N, Cin, H, W, seed=1))
+    wt = rnd(Cout, Cin, k, k, seed=2) * (1.0 / (Cin * k * k) ** 0.5)
+    b = rnd(Cout, seed=3) * 0.1
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    wp = ops.pack_weight(wt, 0)
+    d = make_conv_desc(N, H, W, Cin, 0, Cin, Ho, Wo, Ho, Wo, Cout, 0, Cout, taps_conv(k, p), k * k, wp.shape[1],
+                       wp.shape[2], in_stride=s)
+    rows = igemm_stat_rows(d)
+    if rows == 0 and N * Ho * Wo < 32768:
+        pytest.skip("the tile chooser serves this small shape with the 128-row kernel (no statistics epilogue)")
+    assert rows > 0, "this shape should be served by the statistics epilogue"
+    P = lambda t: C.c_void_p(t.data_ptr())
+    outs = []
+    for rep in range(2):
+        y = torch.zeros(N, Ho, Wo, Cout, dtype=BF, device="cuda")
+        part = torch.full((2 * Cout * rows,), float("nan"), device="cuda")
+        stats, mi = torch.empty(2 * Cout, device="cuda"), torch.empty(2 * Cout, device="cuda")
+        rm, rv = torch.zeros(Cout, device="cuda"), torch.ones(Cout, device="cuda")
+        _lib.check(lib.b200_conv_igemm_stats(C.byref(d), P(x), P(wp), P(b), P(y), P(part), stream_ptr()), "igemm_stats")
+        _lib.check(lib.b200_bn_partials_finalize(P(part), rows, P(stats), P(mi), P(rm), P(rv), N * Ho * Wo, Cout, 0.1, 1e-5,
+                                                 stream_ptr()), "partials_finalize")
+        outs.append((y, stats.clone(), mi.clone(), rm, rv))
+    y, stats, mi, rm, rv = outs[0]
+    assert all(torch.equal(a, b_) for a, b_ in zip(outs[0], outs[1])), "not deterministic"
+    y_plain = ops.conv2d(x, wt, b, stride=s, padding=p)
+    assert torch.equal(y, y_plain)
+    yf = y.float().reshape(-1, Cout)
+    assert rel(stats[:Cout], yf.sum(0)) < 1e-5 and rel(stats[Cout:], (yf * yf).sum(0)) < 1e-5
+    stats2, mi2 = torch.empty(2 * Cout, device="cuda"), torch.empty(2 * Cout, device="cuda")
+    rm2, rv2 = torch.zeros(Cout, device="cuda"), torch.ones(Cout, device="cuda")
+    _lib.check(lib.b200_bn_stats_finalize(P(y), P(stats2), P(mi2), P(rm2), P(rv2), N * Ho * Wo, Cout, 0.1, 1e-5,
+                                          stream_ptr()), "bn_stats_finalize")
+    assert rel(mi, mi2) < 1e-5 and rel(rm, rm2) < 1e-5 and rel(rv, rv2) < 1e-5
+
+
 def test_pools_and_l1():
     from trainner_b200 import ops
     x = F.relu(rnd(2, 64, 16, 24, seed=1))

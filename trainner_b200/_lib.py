@@ -126,6 +126,7 @@ _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 _SIGNATURES = {
     "b200_conv_igemm": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P],
+    "b200_conv_igemm_stats": [_P, _P, _P, _P, _P, _P, _P],
     "b200_conv3x3_flat": [C.POINTER(FlatDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "b200_pack_cat": [_P, _I, _I, _P],
     "b200_rdb_persist": [C.POINTER(RdbDesc), _P, _I, _P],
@@ -145,6 +146,7 @@ _SIGNATURES = {
     "b200_bn_stats": [_P, _P, _L, _I, _P],
     "b200_bn_finalize": [_P, _P, _P, _P, _L, _I, _F, _F, _P],
     "b200_bn_stats_finalize": [_P, _P, _P, _P, _P, _L, _I, _F, _F, _P],
+    "b200_bn_partials_finalize": [_P, _I, _P, _P, _P, _P, _L, _I, _F, _F, _P],
     "b200_bn_apply_lrelu": [_P, _P, _P, _P, _P, _L, _I, _F, _P],
     "b200_bn_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
     "b200_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P],
@@ -164,7 +166,7 @@ _SIGNATURES = {
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["b200_last_error", "b200_version", "b200_device_ok",
                                                 "b200_launch_count", "b200_tensor_map_bytes",
-                                                "b200_wgrad_rdb_ws_bytes"])
+                                                "b200_wgrad_rdb_ws_bytes", "b200_conv_igemm_stat_rows"])
 
 
 def _load():
@@ -183,6 +185,8 @@ def _load():
     lib.b200_launch_count.restype = C.c_int64
     lib.b200_tensor_map_bytes.restype = C.c_int
     lib.b200_tensor_map_bytes.argtypes = []
+    lib.b200_conv_igemm_stat_rows.restype = C.c_int
+    lib.b200_conv_igemm_stat_rows.argtypes = [C.POINTER(ConvDesc)]
     lib.b200_wgrad_rdb_ws_bytes.restype = C.c_int64
     lib.b200_wgrad_rdb_ws_bytes.argtypes = [_I, _I, _I, _I]
     return lib

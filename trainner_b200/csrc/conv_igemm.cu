@@ -55,6 +55,10 @@ struct IgemmParams {
   int dbg;                    // B200_IGEMM_DBG (experiments): 1 skip the epilogue's global traffic
   long long* dbg_ptr;         // B200_IGEMM_DBG_PTR (tools/igemm_timeline.py): CTA 0 stamps clock64() per k-iteration
   CUtensorMap out_map[4];
+  // EPI = 3: per-(tile, half) column sums and sums of squares of the bf16-rounded outputs -- BatchNorm statistics
+  // without a pass over the stored tensor.  Output-major: stat_part[(which * Cout + c) * stat_rows + 2 * pixel_tile + half]
+  float* stat_part;
+  int stat_rows;
   // output placement
   __nv_bfloat16* out;
   long long o_sn, o_sy, o_sx;
@@ -647,6 +651,40 @@ conv_igemm256_kernel(const __grid_constant__ IgemmParams p) {
             }
             bulk_commit_group();
           }
+          if constexpr (EPI == 3) {
+            // column statistics of the staged slab (the values the next layer will read): thread = (column, statistic),
+            // 128 rows in row order; pixels outside the image are excluded.  The buffer is not rewritten before every
+            // thread of this half has passed the "buffer free" barrier of its next use.
+            const int col = m_local & 63, which = m_local >> 6;
+            const int rows_x = p.Wo - tc.x0, rows_y = p.Ho - ty, rows_n = p.Nimg - tn_;
+            float acc_s = 0.f;
+            const uint32_t cbase_s = smem_u32(sbuf) + (uint32_t)((col & 7) * 2);
+            const int hth = p.st_dn ? p.th : p.th / 2, htn = p.st_dn ? p.st_dn : 1;   // the half's rows and images
+            auto ld_col = [&](int r) {
+              uint16_t hv;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(cbase_s + (uint32_t)(r * 128 + (((col >> 3) ^ (r & 7)) << 4))));
+              return __uint_as_float((uint32_t)hv << 16);
+            };
+            if (rows_x >= p.tw && rows_y >= hth && rows_n >= htn) {
+#pragma unroll 8
+              for (int r = 0; r < 128; ++r) {
+                const float f = ld_col(r);
+                acc_s += which ? f * f : f;
+              }
+            } else {
+              for (int r = 0; r < 128; ++r) {
+                const int rx = r % p.tw, ry = (r / p.tw) % hth, rn = r / (p.tw * hth);
+                if (rx >= rows_x || ry >= rows_y || rn >= rows_n) continue;
+                const float f = ld_col(r);
+                acc_s += which ? f * f : f;
+              }
+            }
+            const int cglob = cb + c0 + col;
+            if (cglob < p.Cout) {
+              const int prow = 2 * (tile / p.n_blocks) + half;
+              p.stat_part[((size_t)which * p.Cout + cglob) * p.stat_rows + prow] = acc_s;
+            }
+          }
         }
       } else {
       for (; c0 + 32 <= p.BN; c0 += 32) {
@@ -694,10 +732,12 @@ inline int pow2_ceil(int v) {
 
 using namespace b200;
 
-extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const void* w_packed,
-                               const float* bias, const void* res1, const void* res2,
-                               const void* mask, void* y, b200_stream_t stream) {
-  B200_REQUIRE(d && x && w_packed && y, "b200_conv_igemm: null argument");
+// stat_part != nullptr: also produce the BatchNorm partial statistics (EPI = 3); stat_query != nullptr: launch
+// nothing, only report how many partial rows that would produce (0 = this conv cannot: fall back to b200_bn_stats).
+static int conv_igemm_impl(const b200_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                           const void* res1, const void* res2, const void* mask, void* y, float* stat_part,
+                           int* stat_query, b200_stream_t stream) {
+  B200_REQUIRE(d && (stat_query || (x && w_packed && y)), "b200_conv_igemm: null argument");
   B200_REQUIRE(d->cin > 0 && d->cin % 16 == 0, "b200_conv_igemm: cin=%d must be a multiple of 16", d->cin);
   B200_REQUIRE(d->cout > 0 && d->cout % 8 == 0, "b200_conv_igemm: cout=%d must be a multiple of 8", d->cout);
   B200_REQUIRE(d->cx % 8 == 0 && d->cy % 8 == 0 && d->cin_off % 8 == 0 && d->cout_off % 8 == 0,
@@ -715,6 +755,7 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
   B200_ENSURE_SMEM(conv_igemm256_kernel<0>, kSmem256);
   B200_ENSURE_SMEM(conv_igemm256_kernel<1>, kSmem256);
   B200_ENSURE_SMEM(conv_igemm256_kernel<2>, kSmem256);
+  B200_ENSURE_SMEM(conv_igemm256_kernel<3>, kSmem256);
 
   IgemmParams p;
   memset(&p, 0, sizeof(p));
@@ -827,6 +868,14 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
     }
   }
 
+  const bool stats_ok = p.tma_store && ncls == 1 && !d->upsample2x && !mask && !d->act;
+  if (stat_query) {
+    *stat_query = stats_ok ? 2 * pixel_tiles : 0;
+    return 0;
+  }
+  B200_REQUIRE(!stat_part || stats_ok, "b200_conv_igemm_stats: this conv has no statistics epilogue (ask b200_conv_igemm_stat_rows first)");
+  p.stat_part = stat_part;
+  p.stat_rows = 2 * pixel_tiles;
   // ---- tensor maps
   {
     uint64_t dims[4] = {(uint64_t)(d->cin_off + d->cin), (uint64_t)d->w_in, (uint64_t)d->h_in,
@@ -909,7 +958,9 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (p.tma_store ? 2 * (size_t)p.st_bufs * 128 * 128 : 0);
   const bool fast = p.tma_store != 0;
-  if (use256 && fast && mask)
+  if (use256 && fast && stat_part)
+    ::b200::launch_kernel(conv_igemm256_kernel<3>, grid, kThreads256, smem, as_stream(stream), p);
+  else if (use256 && fast && mask)
     ::b200::launch_kernel(conv_igemm256_kernel<2>, grid, kThreads256, smem, as_stream(stream), p);
   else if (use256 && fast)
     ::b200::launch_kernel(conv_igemm256_kernel<1>, grid, kThreads256, smem, as_stream(stream), p);
@@ -919,4 +970,22 @@ extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const voi
     ::b200::launch_kernel(conv_igemm_kernel, grid, kThreads, smem, as_stream(stream), p);
   B200_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int b200_conv_igemm(const b200_conv_desc* d, const void* x, const void* w_packed,
+                               const float* bias, const void* res1, const void* res2,
+                               const void* mask, void* y, b200_stream_t stream) {
+  return conv_igemm_impl(d, x, w_packed, bias, res1, res2, mask, y, nullptr, nullptr, stream);
+}
+
+extern "C" int b200_conv_igemm_stat_rows(const b200_conv_desc* d) {
+  int rows = 0;
+  if (conv_igemm_impl(d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &rows, nullptr)) return -1;
+  return rows;
+}
+
+extern "C" int b200_conv_igemm_stats(const b200_conv_desc* d, const void* x, const void* w_packed,
+                                     const float* bias, void* y, float* stat_part, b200_stream_t stream) {
+  B200_REQUIRE(stat_part, "b200_conv_igemm_stats: null stat_part");
+  return conv_igemm_impl(d, x, w_packed, bias, nullptr, nullptr, nullptr, y, stat_part, nullptr, stream);
 }

@@ -170,6 +170,38 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, float* __res
   bn_finalize_channel(stats, mean_invstd, running_mean, running_var, npix, c, momentum, eps, ch);
 }
 
+// BatchNorm statistics from the per-tile partial sums the conv epilogue wrote (conv_igemm EPI = 3; output-major
+// part[(which * c + ch) * rows + r]): one warp per channel adds the rows in a fixed order (lane-strided, then a
+// butterfly), so the result is deterministic, then finishes the channel like bn_finalize_kernel.
+__global__ void __launch_bounds__(256) bn_partials_finalize_kernel(const float* __restrict__ part, int rows,
+                                                                   float* __restrict__ stats,
+                                                                   float* __restrict__ mean_invstd,
+                                                                   float* __restrict__ running_mean,
+                                                                   float* __restrict__ running_var, long long npix, int c,
+                                                                   float momentum, float eps) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31, ch = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (ch >= c) return;
+  float s0 = 0.f, s1 = 0.f;
+  const float* p0 = part + (size_t)ch * rows;
+  const float* p1 = part + (size_t)(c + ch) * rows;
+  for (int i = lane; i < rows; i += 32) {
+    s0 += p0[i];
+    s1 += p1[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  if (lane == 0) {
+    stats[ch] = s0;
+    stats[c + ch] = s1;
+    bn_finalize_channel(stats, mean_invstd, running_mean, running_var, npix, c, momentum, eps, ch);
+  }
+}
+
 template <int MODE>  // 0: fwd apply+lrelu ; 1: bwd apply (dz)
 __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z,
                                 const __nv_bfloat16* __restrict__ da,
@@ -564,6 +596,16 @@ int b200_bn_finalize(const float* stats, float* mean_invstd, float* running_mean
                      b200_stream_t stream) {
   ::b200::launch_kernel(bn_finalize_kernel, (c + 127) / 128, 128, 0, as_stream(stream), 
       stats, mean_invstd, running_mean, running_var, npix, c, momentum, eps);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200_bn_partials_finalize(const float* part, int32_t rows, float* stats, float* mean_invstd,
+                              float* running_mean, float* running_var, int64_t npix, int32_t c, float momentum,
+                              float eps, b200_stream_t stream) {
+  B200_REQUIRE(part && stats && mean_invstd && rows > 0, "b200_bn_partials_finalize: bad arguments");
+  ::b200::launch_kernel(bn_partials_finalize_kernel, (c + 7) / 8, 256, 0, as_stream(stream),
+      part, (int)rows, stats, mean_invstd, running_mean, running_var, (long long)npix, (int)c, momentum, eps);
   B200_LAUNCH_CHECK();
   return 0;
 }

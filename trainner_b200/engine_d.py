@@ -7,13 +7,14 @@ Only Z is kept for backward (the activation and its LeakyReLU mask are recompute
 batch statistics).  Every train-mode forward updates running_mean / running_var /
 num_batches_tracked exactly like nn.BatchNorm2d (4 updates per training iteration).
 """
+import os
 import weakref
 
 import torch
 
 from ._lib import lib
 from .runtime import (ConvLayer, ContextPool, pool_for, FlatGrads, Lease, LRELU_SLOPE, P, Plan, WeightPacker,
-                      add_igemm, add_wgrad, make_conv_desc, require_device, taps_conv, taps_dgrad_s1,
+                      add_igemm, add_igemm_stats, igemm_stat_rows, add_wgrad, make_conv_desc, require_device, taps_conv, taps_dgrad_s1,
                       taps_dgrad_s2_k4)
 
 BF16 = torch.bfloat16
@@ -34,6 +35,9 @@ class DiscriminatorEngine:
         # optimizer (models/sr_model.py) switches it on.
         self.reuse = False
         self._cache = {}
+        # BatchNorm batch statistics from the conv epilogue where the conv kernel offers it (B200_BN_FUSE_STATS=0:
+        # always a separate pass over the conv output)
+        self.fuse_stats = os.environ.get("B200_BN_FUSE_STATS", "1") != "0"
 
     def _setup(self, device):
         net = self.net
@@ -67,6 +71,7 @@ class DiscriminatorEngine:
         ctx.x = torch.empty(N, net.in_nc, S, S, dtype=torch.float32, device=dev)
         ctx.A = [e(N, S, S, c0)]
         ctx.Z, ctx.stats, ctx.mi, ctx.dims = [], [], [], []
+        ctx.stat_part = [None] * len(self.layers)
         h = S
         for L, bn in self.layers:
             ho = (h + 2 * L.pad - L.kh) // L.stride + 1
@@ -89,9 +94,18 @@ class DiscriminatorEngine:
                 hi, ho = ctx.dims[i]
                 d = make_conv_desc(N, hi, hi, L.cin, 0, L.cin, ho, ho, ho, ho, L.cout, 0, L.cout,
                                    taps_conv(L.kh, L.pad), L.taps, L.fwd_rows, L.fwd_cols, in_stride=L.stride)
-                add_igemm(f, d, ctx.A[i], L.w_fwd, L.bias, y=ctx.Z[i])
                 npix = N * ho * ho
-                if train:
+                rows = igemm_stat_rows(d) if (train and self.fuse_stats) else 0
+                if rows:
+                    # batch statistics from the conv epilogue (per-tile partial sums) instead of a pass over Z
+                    if ctx.stat_part[i] is None:
+                        ctx.stat_part[i] = torch.empty(2 * L.cout * rows, dtype=torch.float32, device=dev)
+                    add_igemm_stats(f, d, ctx.A[i], L.w_fwd, L.bias, ctx.Z[i], ctx.stat_part[i])
+                    f.add(lib.b200_bn_partials_finalize, P(ctx.stat_part[i]), rows, P(ctx.stats[i]), P(ctx.mi[i]),
+                          P(bn.running_mean), P(bn.running_var), npix, L.cout, float(bn.momentum), float(bn.eps))
+                else:
+                    add_igemm(f, d, ctx.A[i], L.w_fwd, L.bias, y=ctx.Z[i])
+                if train and not rows:
                     f.add(lib.b200_bn_stats_finalize, P(ctx.Z[i]), P(ctx.stats[i]), P(ctx.mi[i]),
                           P(bn.running_mean), P(bn.running_var), npix, L.cout, float(bn.momentum), float(bn.eps))
                 f.add(lib.b200_bn_apply_lrelu, P(ctx.Z[i]), P(ctx.mi[i]), P(bn.weight), P(bn.bias),

@@ -97,6 +97,14 @@ class GradExchange:
         main = torch.cuda.current_stream()
         ready = torch.cuda.Event()
         ready.record(main)
+        # Gradients that are ordinary autograd tensors (the discriminator's classifier: everything outside the flat
+        # buffers) were allocated on the main stream and are dropped by zero_grad(set_to_none=True) inside step_fn --
+        # on the host, long before the side stream has run the optimizer kernels that read them.  Without
+        # record_stream the caching allocator hands their memory to the main stream's next allocations and Adam
+        # reads whatever landed there (found by tools/stress_repro.py: ~1 in 8 runs differed in D's parameters).
+        for p in net.parameters():
+            if p.grad is not None:
+                p.grad.record_stream(self._side)
         with torch.cuda.stream(self._side):
             self._side.wait_event(ready)
             self.all_reduce_grads(net)

@@ -367,6 +367,25 @@ def add_igemm(plan, desc, x, w, bias=None, res1=None, res2=None, mask=None, y=No
              flops=flops, tag="conv_igemm", info=info)
 
 
+def igemm_stat_rows(desc):
+    """Rows of BatchNorm partial statistics the conv's epilogue would write (0: this shape is not served by the
+    statistics epilogue -- run b200_bn_stats_finalize over the output instead)."""
+    r = lib.b200_conv_igemm_stat_rows(C.byref(desc))
+    if r < 0:
+        raise RuntimeError("trainner_b200 conv_igemm_stat_rows failed: %s" % lib.b200_last_error().decode())
+    return r
+
+
+def add_igemm_stats(plan, desc, x, w, bias, y, stat_part):
+    """conv + per-tile BatchNorm partial sums of its bf16 output in one launch (csrc/conv_igemm.cu, EPI = 3)."""
+    plan.keep(desc)
+    flops = 2.0 * desc.n * desc.h_out * desc.w_out * desc.cout * desc.cin * desc.ntaps
+    info = "cin%d cout%d %dx%dx%d taps%d s%d +stats" % (desc.cin, desc.cout, desc.n, desc.h_out, desc.w_out, desc.ntaps,
+                                                         desc.in_stride)
+    plan.add(lib.b200_conv_igemm_stats, C.byref(desc), P(x), P(w), P(bias), P(y), P(stat_part),
+             flops=flops, tag="conv_igemm", info=info)
+
+
 def add_wgrad(plan, n, h_in, w_in, cx, x_coff, cin, h_out, w_out, cdy, dy_coff, cout, k, stride, pad,
               scale, x, dy, dw, db):
     d = WgradDesc(n, h_in, w_in, cx, x_coff, cin, h_out, w_out, cdy, dy_coff, cout, k, k, stride, pad,
