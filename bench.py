@@ -17,6 +17,8 @@ vs_cudnn = the unmodified reference SRModel on this GPU through PyTorch/cuDNN (b
 --impl reference / reference-cudnn run ONLY the reference (they never import trainner_b200 or oracle/).
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -406,4 +408,22 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # stdout carries exactly ONE JSON line: everything else that writes to file descriptor 1 while the bench runs
+    # (NCCL's version banner, the reference's option dumps, library chatter from C code) goes to stderr; the
+    # descriptor is restored when the process is done with everything but the JSON line, which print() buffered.
+    sys.stdout.flush()
+    _saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    _buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(_buf):
+            main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(_saved_fd, 1)
+        os.close(_saved_fd)
+    lines = [l for l in _buf.getvalue().splitlines() if l.strip()]
+    for l in lines[:-1]:
+        print(l, file=sys.stderr)
+    if lines:
+        print(lines[-1], flush=True)
