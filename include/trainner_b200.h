@@ -292,6 +292,20 @@ int b200_bn_finalize(const float* stats, float* mean_invstd, float* running_mean
 int b200_bn_stats_finalize(const void* z, float* stats, float* mean_invstd, float* running_mean,
                            float* running_var, int64_t npix, int32_t c, float momentum, float eps,
                            b200_stream_t stream);
+/* b200_bn_finalize for many layers in one launch (the running-statistics side effect of a re-used train-mode
+ * forward: 11 layers x 2 re-used forwards per step).  table: device array of b200_bn_finalize_entry.            */
+typedef struct {
+  const float* stats;   /* [2][c] sum, sum of squares */
+  float* mean_invstd;   /* [2][c] */
+  float* running_mean;  /* [c] or NULL */
+  float* running_var;   /* [c] or NULL */
+  int64_t npix;
+  int32_t c;
+  float momentum, eps;
+  int32_t pad_;
+} b200_bn_finalize_entry;
+int b200_bn_finalize_multi(const b200_bn_finalize_entry* table_dev, int32_t count, int32_t c_max,
+                           b200_stream_t stream);
 /* BatchNorm statistics from the conv epilogue instead of a pass over z: b200_conv_igemm_stats (below) writes one
  * row of per-channel (sum, sum of squares) per 128-pixel half tile into part[2][c][rows]; this adds the rows in a
  * fixed order and finishes like b200_bn_finalize.  rows = b200_conv_igemm_stat_rows(desc).                      */

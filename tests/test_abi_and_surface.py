@@ -34,6 +34,7 @@ def test_struct_layouts_match_header(tmp_path):
 #include <stddef.h>
 #include "trainner_b200.h"
 int main(void) {
+  printf("%zu %zu ", sizeof(b200_bn_finalize_entry), offsetof(b200_bn_finalize_entry, momentum));
   printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(b200_conv_desc), offsetof(b200_conv_desc, tap_dy),
          offsetof(b200_conv_desc, mask_slope), sizeof(b200_wgrad_desc), sizeof(b200_pack_entry),
          offsetof(b200_pack_entry, cout), sizeof(b200_chain_stage), offsetof(b200_chain_stage, out_c),
@@ -43,7 +44,8 @@ int main(void) {
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
-    want = [ctypes.sizeof(_lib.ConvDesc), _lib.ConvDesc.tap_dy.offset, _lib.ConvDesc.mask_slope.offset,
+    want = [ctypes.sizeof(_lib.BnFinalizeEntry), _lib.BnFinalizeEntry.momentum.offset,
+            ctypes.sizeof(_lib.ConvDesc), _lib.ConvDesc.tap_dy.offset, _lib.ConvDesc.mask_slope.offset,
             ctypes.sizeof(_lib.WgradDesc), ctypes.sizeof(_lib.PackEntry), _lib.PackEntry.cout.offset,
             ctypes.sizeof(_lib.ChainStage), _lib.ChainStage.out_c.offset, _lib.ChainStage.act.offset,
             ctypes.sizeof(_lib.ChainDesc)]

@@ -75,6 +75,12 @@ class ColsumEntry(C.Structure):
                 ("pitch", C.c_int32), ("coff", C.c_int32), ("c", C.c_int32), ("scale", C.c_float)]
 
 
+class BnFinalizeEntry(C.Structure):
+    _fields_ = [("stats", C.c_void_p), ("mean_invstd", C.c_void_p), ("running_mean", C.c_void_p),
+                ("running_var", C.c_void_p), ("npix", C.c_int64), ("c", C.c_int32), ("momentum", C.c_float),
+                ("eps", C.c_float), ("pad_", C.c_int32)]
+
+
 class PackCatEntry(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p),
                 ("cout", C.c_int32), ("cin", C.c_int32), ("taps", C.c_int32), ("ci_off", C.c_int32),
@@ -147,6 +153,7 @@ _SIGNATURES = {
     "b200_bn_finalize": [_P, _P, _P, _P, _L, _I, _F, _F, _P],
     "b200_bn_stats_finalize": [_P, _P, _P, _P, _P, _L, _I, _F, _F, _P],
     "b200_bn_partials_finalize": [_P, _I, _P, _P, _P, _P, _L, _I, _F, _F, _P],
+    "b200_bn_finalize_multi": [_P, _I, _I, _P],
     "b200_bn_apply_lrelu": [_P, _P, _P, _P, _P, _L, _I, _F, _P],
     "b200_bn_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
     "b200_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P],

@@ -170,6 +170,15 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, float* __res
   bn_finalize_channel(stats, mean_invstd, running_mean, running_var, npix, c, momentum, eps, ch);
 }
 
+__global__ void bn_finalize_multi_kernel(const b200_bn_finalize_entry* __restrict__ table) {
+  pdl_trigger();
+  pdl_wait();
+  const b200_bn_finalize_entry e = table[blockIdx.y];
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= e.c) return;
+  bn_finalize_channel(e.stats, e.mean_invstd, e.running_mean, e.running_var, e.npix, e.c, e.momentum, e.eps, ch);
+}
+
 // BatchNorm statistics from the per-tile partial sums the conv epilogue wrote (conv_igemm EPI = 3; output-major
 // part[(which * c + ch) * rows + r]): one warp per channel adds the rows in a fixed order (lane-strided, then a
 // butterfly), so the result is deterministic, then finishes the channel like bn_finalize_kernel.
@@ -596,6 +605,15 @@ int b200_bn_finalize(const float* stats, float* mean_invstd, float* running_mean
                      b200_stream_t stream) {
   ::b200::launch_kernel(bn_finalize_kernel, (c + 127) / 128, 128, 0, as_stream(stream), 
       stats, mean_invstd, running_mean, running_var, npix, c, momentum, eps);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200_bn_finalize_multi(const b200_bn_finalize_entry* table_dev, int32_t count, int32_t c_max,
+                           b200_stream_t stream) {
+  if (count <= 0) return 0;
+  B200_REQUIRE(table_dev && c_max > 0, "b200_bn_finalize_multi: bad arguments");
+  ::b200::launch_kernel(bn_finalize_multi_kernel, dim3((c_max + 127) / 128, count), 128, 0, as_stream(stream), table_dev);
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -12,7 +12,7 @@ import weakref
 
 import torch
 
-from ._lib import lib
+from ._lib import BnFinalizeEntry, lib
 from .runtime import (ConvLayer, ContextPool, pool_for, FlatGrads, Lease, LRELU_SLOPE, P, Plan, WeightPacker,
                       add_igemm, add_igemm_stats, igemm_stat_rows, add_wgrad, make_conv_desc, require_device, taps_conv, taps_dgrad_s1,
                       taps_dgrad_s2_k4)
@@ -115,10 +115,13 @@ class DiscriminatorEngine:
 
         ctx.fwd_train = fwd_plan(True)
         ctx.fwd_eval = fwd_plan(False)
-        rf = Plan()   # the running-stat side effect of a train-mode forward, replayed on forward reuse
-        for i, (L, bn) in enumerate(self.layers):
-            rf.add(lib.b200_bn_finalize, P(ctx.stats[i]), P(ctx.mi[i]), P(bn.running_mean), P(bn.running_var),
-                   N * ctx.dims[i][1] * ctx.dims[i][1], L.cout, float(bn.momentum), float(bn.eps))
+        rf = Plan()   # the running-stat side effect of a train-mode forward, replayed on forward reuse: ONE launch
+        ents = [BnFinalizeEntry(ctx.stats[i].data_ptr(), ctx.mi[i].data_ptr(), bn.running_mean.data_ptr(),
+                                bn.running_var.data_ptr(), N * ctx.dims[i][1] * ctx.dims[i][1], L.cout,
+                                float(bn.momentum), float(bn.eps), 0) for i, (L, bn) in enumerate(self.layers)]
+        ctx.refinalize_table = torch.frombuffer(bytearray(bytes((BnFinalizeEntry * len(ents))(*ents))),
+                                                dtype=torch.uint8).to(dev)
+        rf.add(lib.b200_bn_finalize_multi, P(ctx.refinalize_table), len(ents), max(L.cout for L, _ in self.layers))
         ctx.refinalize = rf
         ctx.bwd = {}
         return ctx
