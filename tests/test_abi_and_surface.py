@@ -25,6 +25,33 @@ def test_library_exports_every_declared_symbol():
     assert lib.b200_version() >= 100
 
 
+def test_ctypes_signatures_have_the_declared_arity():
+    """Every entry point's ctypes argtypes list (trainner_b200/_lib.py) has as many arguments as its declaration in
+    include/trainner_b200.h, pointers where the header has pointers and 64-bit integers where it has int64_t."""
+    from trainner_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "trainner_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    checked = 0
+    for name, params in re.findall(r"\bint(?:64_t)?\s+(b200_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr):
+        sig = _lib._SIGNATURES.get(name)
+        if sig is None:
+            continue
+        plist = [q.strip() for q in params.split(",") if q.strip() and q.strip() != "void"]
+        assert len(plist) == len(sig), "%s: header has %d parameters, ctypes %d" % (name, len(plist), len(sig))
+        for q, ct in zip(plist, sig):
+            is_ptr = "*" in q or q.startswith("b200_stream_t")
+            if is_ptr:
+                assert ct is ctypes.c_void_p or isinstance(ct, type(ctypes.POINTER(ctypes.c_int))), (name, q, ct)
+            elif q.startswith("int64_t"):
+                assert ct is ctypes.c_int64, (name, q, ct)
+            elif q.startswith("float"):
+                assert ct is ctypes.c_float, (name, q, ct)
+            elif q.startswith("int32_t") or q.startswith("int "):
+                assert ct is ctypes.c_int32 or ct is ctypes.c_int, (name, q, ct)
+        checked += 1
+    assert checked >= 25
+
+
 def test_struct_layouts_match_header(tmp_path):
     """sizeof/offsetof as the C compiler sees include/trainner_b200.h == the ctypes mirrors."""
     import subprocess
